@@ -1,0 +1,169 @@
+/* lqcd_b200.h -- C ABI of the B200-native pure-gauge SU(3) update path.
+ *
+ * Drop-in boundary for lattice-qcd-rs v0.2.1 (a pure-Rust crate with no FFI of its own: README.md:32 lists a
+ * "C friendly API / ABI" as not implemented).  Each entry point below names the reference loop it replaces
+ * (file:line under /root/reference/src).  A Rust shim crate (rust/lattice-qcd-b200, authored)
+ * binds exactly these symbols and implements the crate's traits on top of them.
+ *
+ * Conventions
+ *   - every function returns 0 (LQ_OK) or a negative LQ_E_* code; nothing unwinds across the ABI.
+ *   - host pointers are borrowed for the duration of the call; the context owns all device memory.
+ *   - a context is bound to one CUDA device and one stream; calls on one context are not re-entrant
+ *     (matches the reference, where a state value is moved through `next_element` by one thread).
+ *   - array layouts at the boundary are the reference's own AoS layouts:
+ *       links  : n_links * 18 f64, link = site*D + dir, 3x3 complex column-major (re,im)  field.rs:584-586
+ *       efield : n_links *  8 f64, (site*D + dir)*8 + a                                   field.rs:1025-1027
+ *       site   : sum_k x_k * prod_{l<k} extent_l   (x_0 fastest)                          lattice.rs:909-916
+ *     On a decomposed (multi-rank) context "site" enumerates the rank-local block in the same order.
+ *   - all arithmetic is f64 (lib.rs:69 `Real = f64`).
+ */
+#ifndef LQCD_B200_H
+#define LQCD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lq_ctx lq_ctx;
+
+enum {
+  LQ_OK = 0,
+  LQ_E_BADARG = -1,         /* null pointer, D out of range, extent < 2 (lattice.rs:190-201)            */
+  LQ_E_SIZE = -2,           /* StateInitializationError::IncompatibleSize (state.rs:784-786)             */
+  LQ_E_CUDA = -3,           /* any CUDA runtime failure (lq_last_cuda_error has the text)                */
+  LQ_E_COMM = -4,           /* halo transport failure                                                    */
+  LQ_E_ODD_EXTENT = -5,     /* checkerboard sweeps need even extents in every direction                  */
+  LQ_E_GAUSS_DIVERGED = -6, /* StateInitializationError::GaussProjectionError (field.rs:1279-1281)       */
+  LQ_E_ZERO_STEPS = -7,     /* MultiIntegrationError::ZeroIntegration (state.rs:331-333, 480-482)        */
+  LQ_E_NOSNAPSHOT = -8,
+  LQ_E_NODEVICE = -9        /* no CUDA device: there is NO CPU fallback                                  */
+};
+
+/* integrator compositions, symplectic_euler_rayon.rs:120-252 */
+enum { LQ_SYNC_SYNC = 0, LQ_LEAP_LEAP = 1, LQ_SYNC_LEAP = 2, LQ_LEAP_SYNC = 3, LQ_SYMPLECTIC = 4 };
+/* over-relaxation flavours, overrelaxation.rs:86-98 / 158-171 */
+enum { LQ_OR_ROTATION = 0, LQ_OR_REVERSE = 1 };
+/* behaviour flags (lq_set_flags) */
+enum {
+  LQ_FLAG_PAULI3_FIXED = 1,   /* use sigma_3 = diag(1,-1); default restates su2.rs:39-45 as coded (diag(1,1)) */
+  LQ_FLAG_NO_KICK_MERGE = 2   /* lq_symplectic_n: do not merge the two adjacent dt/2 E-kicks of consecutive steps
+                                 (results are bit-identical either way; this only changes the launch count)    */
+};
+
+const char* lq_strerror(int code);
+const char* lq_last_cuda_error(void);
+int lq_version(void);
+int lq_device_count(int* n);
+
+/* ---- context ------------------------------------------------------------------------------------------------
+ * LatticeCyclic::new (lattice.rs:190-201) + LatticeStateDefault/LatticeStateEFSyncDefault storage
+ * (state.rs:655-659, 1048-1062).  `extent[D]` may differ per direction (the reference has a single `dim`). */
+int lq_ctx_create(lq_ctx** out, int device, int D, const int64_t* extent, double lattice_spacing_a, double beta,
+                  double CA);
+/* Decomposed context: `global_extent[D]` split over `proc_grid[D]` ranks (only the last two directions may be
+ * split); `rank_coord[D]` is this rank's position.  One-site-deep ghost layers are kept in the split directions
+ * and filled through lq_halo_* (host-staged or peer-mapped transport supplied by the caller's plumbing). */
+int lq_ctx_create_dist(lq_ctx** out, int device, int D, const int64_t* global_extent, const int* proc_grid,
+                       const int* rank_coord, double lattice_spacing_a, double beta, double CA);
+int lq_ctx_destroy(lq_ctx*);
+int lq_set_flags(lq_ctx*, int flags);
+int lq_get_flags(lq_ctx*, int* flags);
+int lq_set_beta(lq_ctx*, double beta);
+int lq_sync(lq_ctx*);                              /* cudaStreamSynchronize on the context stream */
+int lq_stream(lq_ctx*, void** cuda_stream_out);    /* the context's cudaStream_t (for CUDA-event timing by the caller) */
+int64_t lq_num_sites(const lq_ctx*);               /* rank-local interior sites  (lattice.rs number_of_points)    */
+int64_t lq_num_links(const lq_ctx*);               /* rank-local interior links  (number_of_canonical_links_space) */
+int64_t lq_t(const lq_ctx*);                       /* LatticeStateWithEField::t  (state.rs:1060)                   */
+int lq_set_t(lq_ctx*, int64_t t);
+int64_t lq_kernel_launches(const lq_ctx*);         /* number of kernels this context has launched so far         */
+
+/* ---- boundary marshalling (LatticeStateNew::new state.rs:779-792; set_link_matrix :808-815) ----------------- */
+int lq_links_upload(lq_ctx*, const double* aos, int64_t n_links);   /* LQ_E_SIZE if n_links mismatches */
+int lq_links_download(lq_ctx*, double* aos, int64_t n_links);
+int lq_efield_upload(lq_ctx*, const double* aos, int64_t n_links);
+int lq_efield_download(lq_ctx*, double* aos, int64_t n_links);
+/* same, from / to DEVICE memory already in the reference AoS layout (no PCIe copy) */
+int lq_links_upload_device(lq_ctx*, const double* d_aos, int64_t n_links);
+int lq_links_download_device(lq_ctx*, double* d_aos, int64_t n_links);
+int lq_efield_upload_device(lq_ctx*, const double* d_aos, int64_t n_links);
+int lq_efield_download_device(lq_ctx*, double* d_aos, int64_t n_links);
+int lq_links_set_cold(lq_ctx*);                    /* LatticeStateDefault::new_cold, state.rs:671-679   */
+int lq_efield_set_zero(lq_ctx*);                   /* EField::new_cold, field.rs:1102-1106              */
+/* LinkMatrix::new_determinist (field.rs:646-659): random_su3 per link from Philox stream (seed, counter, link) */
+int lq_links_set_random(lq_ctx*, uint64_t seed, uint64_t counter);
+
+/* ---- observables ------------------------------------------------------------------------------------------- */
+/* sum_x sum_{i<j} Tr P_ij(x): numerator of average_trace_plaquette (field.rs:775-804; state.rs:115-117) */
+int lq_plaquette_sum(lq_ctx*, double out_re_im[2]);
+int lq_average_trace_plaquette(lq_ctx*, double out_re_im[2]);
+int lq_hamiltonian_links(lq_ctx*, double* h);      /* state.rs:821-849  */
+int lq_hamiltonian_efield(lq_ctx*, double* h);     /* state.rs:1370-1385 */
+int lq_hamiltonian_total(lq_ctx*, double* h);      /* state.rs:229-231  */
+
+/* ---- molecular dynamics ------------------------------------------------------------------------------------ */
+int lq_staples(lq_ctx*, double* aos_out, int64_t n_links);   /* staple(), monte_carlo/mod.rs:339-362 (parity/debug) */
+int lq_force(lq_ctx*, double* aos_out, int64_t n_links);     /* derivative_e, state.rs:1420-1448 (dE/dt, no update) */
+int lq_efield_step(lq_ctx*, double dt);            /* integrate_efield over the lattice, integrator/mod.rs:240-254 */
+int lq_link_step(lq_ctx*, double dt, int use_exp); /* integrate_link, integrator/mod.rs:216-233 (use_exp=0: Euler)  */
+int lq_integrate(lq_ctx*, int kind, double dt);    /* one composition; t += 1 except LQ_SYNC_LEAP                  */
+/* simulate_symplectic_n, state.rs:470-492: n x (E dt/2, U dt, E dt/2) */
+int lq_symplectic_n(lq_ctx*, double dt, int64_t n_steps);
+/* simulate_using_leapfrog_n, state.rs:321-358: sync_leap, (n-1) x leap_leap, leap_sync */
+int lq_leapfrog_n(lq_ctx*, double dt, int64_t n_steps);
+int lq_reunitarize(lq_ctx*);                       /* normalize_link_matrices, state.rs:754-756; su3.rs:279-303 */
+
+/* ---- momenta + Gauss law ----------------------------------------------------------------------------------- */
+/* EField::new_determinist with Normal(0, sigma) (field.rs:1086-1099; state.rs:1097 sigma = 0.5/beta) */
+int lq_momenta_refresh(lq_ctx*, uint64_t seed, uint64_t counter, double sigma);
+int lq_gauss_field(lq_ctx*, double* aos_out, int64_t n_sites);  /* EField::gauss, field.rs:1174-1195 (n_sites*18) */
+int lq_gauss_sum_div(lq_ctx*, double* out);        /* field.rs:1199-1220 */
+int lq_gauss_project_step(lq_ctx*);                /* field.rs:1301-1337 */
+int lq_gauss_project(lq_ctx*, int64_t max_steps, int64_t* steps_out);  /* field.rs:1265-1294 */
+
+/* ---- local-update sweeps (even/odd checkerboard; visit order: for dir, for parity) -------------------------- */
+int lq_sweep_heatbath(lq_ctx*, uint64_t seed, uint64_t counter, double coupling_scale); /* heat_bath.rs:73-123 */
+int lq_sweep_overrelax(lq_ctx*, int kind);                                              /* overrelaxation.rs    */
+int lq_sweep_metropolis(lq_ctx*, uint64_t seed, uint64_t counter, double spread, int n_update, int64_t* n_accept,
+                        double* sum_prob);                              /* metropolis_hastings_sweep.rs:126-174 */
+
+/* ---- HMC (hybrid_monte_carlo.rs:465-471, 573-613) ----------------------------------------------------------- */
+int lq_snapshot(lq_ctx*);                          /* keep (U,E,t) on the device for the reject path */
+int lq_restore(lq_ctx*);
+/* refresh (unless use_current_e) -> optional Gauss projection -> H_old -> n symplectic steps -> H_new ->
+ * Bernoulli(clamp(exp(H_old-H_new),0,1)) from Philox stream (seed, counter, 0xFFFFFFFFFE); on reject the links
+ * (and t) are restored.  On a decomposed context the energies returned are rank-local partial sums and NO accept
+ * decision is taken (accept_mode = 0); the caller all-reduces and calls lq_restore itself. */
+int lq_hmc_trajectory(lq_ctx*, double dt, int64_t n_steps, uint64_t seed, uint64_t counter, double sigma,
+                      int use_current_e, int do_project, double* h_old, double* h_new, double* prob, int* accepted,
+                      int64_t* gauss_steps);
+
+/* ---- decomposed contexts: ghost layers and global sums ------------------------------------------------------
+ * The library sequences every kernel itself; the caller's plumbing (torch.distributed over NCCL/NVLink, one
+ * process per GPU) only moves bytes.  It registers two callbacks:
+ *   halo_exchange(user, ctx, which): refresh the ghost layers of field `which` (0 links, 1 efield, 2 gauss field):
+ *       for every decomposed direction in ascending order: lq_halo_pack both faces into caller-owned device
+ *       buffers, send/recv them to the two neighbours, lq_halo_unpack into the ghost layers.
+ *   allreduce_sum(user, vals, n): in-place sum of n host doubles over all ranks.
+ * With both set, every reduction (plaquette, Hamiltonians, Gauss residual, Metropolis statistics) returns the
+ * GLOBAL value on every rank and lq_hmc_trajectory takes the same accept decision everywhere. */
+typedef struct lq_comm {
+  void* user;
+  int (*halo_exchange)(void* user, lq_ctx* ctx, int which);
+  int (*allreduce_sum)(void* user, double* vals, int n);
+} lq_comm;
+int lq_set_comm(lq_ctx*, const lq_comm* comm);
+/* run all context work on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the private one */
+int lq_set_stream(lq_ctx*, void* cuda_stream);
+int lq_is_decomposed(const lq_ctx*, int dir);     /* 1 if `dir` carries ghost layers */
+int lq_halo_bytes(lq_ctx*, int which, int dir, int64_t* bytes);
+/* side: 0 = low face, 1 = high face.  pack reads the interior boundary slice, unpack writes the ghost slice. */
+int lq_halo_pack(lq_ctx*, int which, int dir, int side, void* d_buf, int64_t bytes);
+int lq_halo_unpack(lq_ctx*, int which, int dir, int side, const void* d_buf, int64_t bytes);
+int lq_halo_invalidate(lq_ctx*, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQCD_B200_H */

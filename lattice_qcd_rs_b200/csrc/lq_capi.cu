@@ -1,0 +1,1029 @@
+// lq_capi.cu -- context, kernel launchers and the extern "C" surface declared in include/lqcd_b200.h.
+//
+// Default build: CUDA for sm_100a (nvcc -gencode arch=compute_100a,code=sm_100a).  There is no CPU path in that
+// library: without a device lq_ctx_create returns LQ_E_NODEVICE.
+// -DLQ_HOST_EMU (g++ -x c++): the same kernel bodies in host loops -- test infrastructure for the CPU CI only
+// (tests/emu.py); the package never loads it.
+#include "../../include/lqcd_b200.h"
+#include "lq_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#if !defined(LQ_HOST_EMU) && defined(LQ_HAVE_TUNED)
+#include "lq_tuned.cuh"
+#define LQ_TUNED 1
+#endif
+
+#define LQ_BLOCK 128
+#define LQ_RBLOCK 256
+
+static thread_local char g_cuda_err[512] = "";
+
+// ------------------------------------------------------------------------------------------------ runtime shim
+#ifdef LQ_HOST_EMU
+typedef void* lq_stream_t;
+#define LQ_CHECK(x) \
+  do {              \
+  } while (0)
+static int rt_malloc(void** p, size_t n) {
+  *p = calloc(n ? n : 1, 1);
+  return *p ? LQ_OK : LQ_E_CUDA;
+}
+static void rt_free(void* p) { free(p); }
+static int rt_malloc_host(void** p, size_t n) { return rt_malloc(p, n); }
+static void rt_free_host(void* p) { free(p); }
+static int rt_copy(void* d, const void* s, size_t n, int /*kind*/, lq_stream_t) {
+  memcpy(d, s, n);
+  return LQ_OK;
+}
+static int rt_memset(void* d, int v, size_t n, lq_stream_t) {
+  memset(d, v, n);
+  return LQ_OK;
+}
+static int rt_sync(lq_stream_t) { return LQ_OK; }
+enum { H2D = 0, D2H = 1, D2D = 2 };
+#else
+typedef cudaStream_t lq_stream_t;
+static int cuda_fail(cudaError_t e, const char* what, int line) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s failed at lq_capi.cu:%d: %s", what, line, cudaGetErrorString(e));
+  return LQ_E_CUDA;
+}
+#define LQ_CHECK(x)                                              \
+  do {                                                           \
+    cudaError_t e_ = (x);                                        \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #x, __LINE__);   \
+  } while (0)
+static int rt_malloc(void** p, size_t n) {
+  LQ_CHECK(cudaMalloc(p, n ? n : 1));
+  return LQ_OK;
+}
+static void rt_free(void* p) {
+  if (p) cudaFree(p);
+}
+static int rt_malloc_host(void** p, size_t n) {
+  LQ_CHECK(cudaMallocHost(p, n));
+  return LQ_OK;
+}
+static void rt_free_host(void* p) {
+  if (p) cudaFreeHost(p);
+}
+enum { H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost, D2D = cudaMemcpyDeviceToDevice };
+static int rt_copy(void* d, const void* s, size_t n, int kind, lq_stream_t st) {
+  LQ_CHECK(cudaMemcpyAsync(d, s, n, (cudaMemcpyKind)kind, st));
+  return LQ_OK;
+}
+static int rt_memset(void* d, int v, size_t n, lq_stream_t st) {
+  LQ_CHECK(cudaMemsetAsync(d, v, n, st));
+  return LQ_OK;
+}
+static int rt_sync(lq_stream_t st) {
+  LQ_CHECK(cudaStreamSynchronize(st));
+  return LQ_OK;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------ context
+struct lq_ctx {
+  int device;
+  lq_stream_t stream;
+  bool own_stream;
+  LqGeom g;
+  double a, beta, CA;
+  int flags;
+  int64_t t;
+  int64_t launches;
+  bool decomposed;
+  int nproc[LQ_MAXD];
+  bool even_extents;
+  cx *U, *U2, *E, *E2, *G;
+  cx *snapU, *snapE;
+  int64_t snap_t;
+  bool has_snap;
+  double* d_aos;
+  size_t d_aos_bytes;
+  double* d_partial;
+  size_t partial_cap;  // doubles
+  double* d_result;
+  double* h_result;
+  bool halo_ok[3];
+  lq_comm comm;
+  bool has_comm;
+  size_t u_bytes() const { return (size_t)g.pitch * 9 * g.D * sizeof(cx); }
+  size_t e_bytes() const { return (size_t)g.pitch * 4 * g.D * sizeof(cx); }
+  size_t g_bytes() const { return (size_t)g.pitch * 9 * sizeof(cx); }
+};
+
+#ifndef LQ_HOST_EMU
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) {
+    ok = cudaGetDevice(&prev) == cudaSuccess;
+    if (ok && prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (ok) cudaSetDevice(prev);
+  }
+};
+#define LQ_GUARD(c) DeviceGuard guard_((c)->device)
+#else
+#define LQ_GUARD(c) \
+  do {              \
+  } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------------ launchers
+#ifdef LQ_HOST_EMU
+template <class F>
+static int launch(lq_ctx* c, lq_i64 n, const F& f) {
+  c->launches++;
+#pragma omp parallel for schedule(static)
+  for (lq_i64 i = 0; i < n; ++i) f(i);
+  return LQ_OK;
+}
+// result lands in c->h_result[0..K)
+template <class F>
+static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
+  c->launches += 2;
+  double acc[F::K];
+  for (int k = 0; k < F::K; ++k) acc[k] = 0.0;
+  for (lq_i64 b = 0; b < n; b += LQ_RBLOCK) {
+    double v[F::K];
+    for (int k = 0; k < F::K; ++k) v[k] = 0.0;
+    for (lq_i64 i = b; i < n && i < b + LQ_RBLOCK; ++i) f(i, v);
+    for (int k = 0; k < F::K; ++k) acc[k] += v[k];
+  }
+  for (int k = 0; k < F::K; ++k) c->h_result[k] = acc[k];
+  return LQ_OK;
+}
+#else
+template <class F>
+__global__ void __launch_bounds__(LQ_BLOCK) lq_k(F f, lq_i64 n) {
+  lq_i64 i = (lq_i64)blockIdx.x * LQ_BLOCK + threadIdx.x;
+  if (i < n) f(i);
+}
+template <class F>
+__global__ void __launch_bounds__(LQ_RBLOCK) lq_reduce_k(F f, lq_i64 n, double* partial) {
+  constexpr int K = F::K;
+  double v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = 0.0;
+  lq_i64 i = (lq_i64)blockIdx.x * LQ_RBLOCK + threadIdx.x;
+  if (i < n) f(i, v);
+  __shared__ double sm[K][LQ_RBLOCK / 32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) sm[k][w] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double x = 0.0;
+#pragma unroll
+    for (int j = 0; j < LQ_RBLOCK / 32; ++j) x += sm[threadIdx.x][j];
+    partial[(lq_i64)blockIdx.x * K + threadIdx.x] = x;
+  }
+}
+// fixed-order final sum of the per-block partials (deterministic: no atomics)
+template <int K>
+__global__ void __launch_bounds__(LQ_RBLOCK) lq_final_k(const double* partial, lq_i64 nblk, double* out) {
+  __shared__ double sm[K][LQ_RBLOCK];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double x = 0.0;
+    for (lq_i64 b = threadIdx.x; b < nblk; b += LQ_RBLOCK) x += partial[b * K + k];
+    sm[k][threadIdx.x] = x;
+  }
+  __syncthreads();
+  for (int o = LQ_RBLOCK / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < K) out[threadIdx.x] = sm[threadIdx.x][0];
+}
+template <class F>
+static int launch(lq_ctx* c, lq_i64 n, const F& f) {
+  if (n <= 0) return LQ_OK;
+  lq_i64 nb = (n + LQ_BLOCK - 1) / LQ_BLOCK;
+  lq_k<F><<<(unsigned)nb, LQ_BLOCK, 0, c->stream>>>(f, n);
+  c->launches++;
+  LQ_CHECK(cudaGetLastError());
+  return LQ_OK;
+}
+template <class F>
+static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
+  constexpr int K = F::K;
+  lq_i64 nb = (n + LQ_RBLOCK - 1) / LQ_RBLOCK;
+  if ((size_t)(nb * K) > c->partial_cap) {
+    rt_free(c->d_partial);
+    c->d_partial = nullptr;
+    int rc = rt_malloc((void**)&c->d_partial, (size_t)nb * K * sizeof(double));
+    if (rc) return rc;
+    c->partial_cap = (size_t)nb * K;
+  }
+  lq_reduce_k<F><<<(unsigned)nb, LQ_RBLOCK, 0, c->stream>>>(f, n, c->d_partial);
+  lq_final_k<K><<<1, LQ_RBLOCK, 0, c->stream>>>(c->d_partial, nb, c->d_result);
+  c->launches += 2;
+  LQ_CHECK(cudaGetLastError());
+  int rc = rt_copy(c->h_result, c->d_result, K * sizeof(double), D2H, c->stream);
+  if (rc) return rc;
+  return rt_sync(c->stream);
+}
+#endif
+
+#define LQ_DISPATCH(c, CALL)          \
+  switch ((c)->g.D) {                 \
+    case 2: { constexpr int DD = 2; CALL; } break; \
+    case 3: { constexpr int DD = 3; CALL; } break; \
+    case 4: { constexpr int DD = 4; CALL; } break; \
+    default: return LQ_E_BADARG;      \
+  }
+
+#define LQ_TRY(x)          \
+  do {                     \
+    int rc_ = (x);         \
+    if (rc_) return rc_;   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ helpers
+static int ensure_halo(lq_ctx* c, int which) {
+  if (!c->decomposed || c->halo_ok[which]) return LQ_OK;
+  if (!c->has_comm || !c->comm.halo_exchange) return LQ_E_COMM;
+  int rc = c->comm.halo_exchange(c->comm.user, c, which);
+  if (rc) return LQ_E_COMM;
+  c->halo_ok[which] = true;
+  return LQ_OK;
+}
+static int global_sum(lq_ctx* c, double* v, int n) {
+  if (!c->decomposed) return LQ_OK;
+  if (!c->has_comm || !c->comm.allreduce_sum) return LQ_OK;  // rank-local partial sums
+  return c->comm.allreduce_sum(c->comm.user, v, n) ? LQ_E_COMM : LQ_OK;
+}
+static lq_i64 global_sites(const lq_ctx* c) {
+  lq_i64 n = 1;
+  for (int d = 0; d < c->g.D; ++d) n *= c->g.gext[d];
+  return n;
+}
+static int ensure_aos(lq_ctx* c, size_t bytes) {
+  if (c->d_aos_bytes >= bytes) return LQ_OK;
+  rt_free(c->d_aos);
+  c->d_aos = nullptr;
+  c->d_aos_bytes = 0;
+  LQ_TRY(rt_malloc((void**)&c->d_aos, bytes));
+  c->d_aos_bytes = bytes;
+  return LQ_OK;
+}
+static int ensure_buf(cx** p, size_t bytes, lq_ctx* c) {
+  if (*p) return LQ_OK;
+  LQ_TRY(rt_malloc((void**)p, bytes));
+  return rt_memset(*p, 0, bytes, c->stream);
+}
+
+static int init_geom(LqGeom& g, int D, const int64_t* gext, const int* nproc, const int* coord) {
+  if (D < 2 || D > LQ_MAXD) return LQ_E_BADARG;
+  memset(&g, 0, sizeof(g));
+  g.D = D;
+  lq_i64 ss = 1, gs = 1, ls = 1;
+  for (int d = 0; d < LQ_MAXD; ++d) {
+    if (d < D) {
+      if (gext[d] < 2 || gext[d] > (1 << 20)) return LQ_E_BADARG;  // LatticeCyclic::new needs dim >= 2 (lattice.rs:190-201)
+      int np = nproc ? nproc[d] : 1;
+      if (np < 1 || gext[d] % np != 0) return LQ_E_BADARG;
+      if (np > 1 && d < D - 2) return LQ_E_BADARG;  // only the two slowest directions may be split
+      if (np > 1 && d == 0) return LQ_E_BADARG;
+      g.gext[d] = (int)gext[d];
+      g.ext[d] = (int)(gext[d] / np);
+      if (np > 1 && g.ext[d] < 2) return LQ_E_BADARG;
+      g.ghost[d] = np > 1 ? 1 : 0;
+      g.goff[d] = np > 1 ? coord[d] * g.ext[d] : 0;
+      if (np > 1 && (coord[d] < 0 || coord[d] >= np)) return LQ_E_BADARG;
+    } else {
+      g.gext[d] = g.ext[d] = 1;
+      g.ghost[d] = 0;
+      g.goff[d] = 0;
+    }
+    g.sext[d] = g.ext[d] + 2 * g.ghost[d];
+    g.sstride[d] = ss;
+    g.gstride[d] = gs;
+    g.lstride[d] = ls;
+    ss *= g.sext[d];
+    gs *= g.gext[d];
+    ls *= g.ext[d];
+  }
+  g.vol = ls;
+  g.svol = ss;
+  g.half = ((g.svol + 1) / 2 + 7) & ~(lq_i64)7;  // keep the odd half 128-byte aligned
+  g.pitch = 2 * g.half;
+  g.ne0 = (g.ext[0] + 1) / 2;
+  return LQ_OK;
+}
+
+static int ctx_create_common(lq_ctx** out, int device, int D, const int64_t* gext, const int* nproc, const int* coord,
+                             double a, double beta, double CA) {
+  if (!out || !gext) return LQ_E_BADARG;
+  *out = nullptr;
+  LqGeom g;
+  LQ_TRY(init_geom(g, D, gext, nproc, coord));
+#ifndef LQ_HOST_EMU
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "no CUDA device visible; this library has no CPU fallback");
+    return LQ_E_NODEVICE;
+  }
+  if (device < 0 || device >= ndev) return LQ_E_BADARG;
+#endif
+  lq_ctx* c = new (std::nothrow) lq_ctx();
+  if (!c) return LQ_E_CUDA;
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->g = g;
+  c->a = a;
+  c->beta = beta;
+  c->CA = CA;
+  c->decomposed = false;
+  c->even_extents = true;
+  for (int d = 0; d < LQ_MAXD; ++d) {
+    c->nproc[d] = (nproc && d < D) ? nproc[d] : 1;
+    if (c->nproc[d] > 1) c->decomposed = true;
+    if (d < D && (g.gext[d] & 1 || g.ext[d] & 1)) c->even_extents = false;
+  }
+  int rc = LQ_OK;
+#ifndef LQ_HOST_EMU
+  DeviceGuard guard(device);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) rc = LQ_E_CUDA;
+  c->own_stream = true;
+#endif
+  if (!rc) rc = rt_malloc((void**)&c->U, c->u_bytes());
+  if (!rc) rc = rt_malloc((void**)&c->E, c->e_bytes());
+  if (!rc) rc = rt_malloc((void**)&c->d_result, 16 * sizeof(double));
+  if (!rc) rc = rt_malloc_host((void**)&c->h_result, 16 * sizeof(double));
+  if (!rc) rc = rt_memset(c->U, 0, c->u_bytes(), c->stream);
+  if (!rc) rc = rt_memset(c->E, 0, c->e_bytes(), c->stream);
+  if (rc) {
+    lq_ctx_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return LQ_OK;
+}
+
+extern "C" {
+
+const char* lq_strerror(int code) {
+  switch (code) {
+    case LQ_OK: return "ok";
+    case LQ_E_BADARG: return "bad argument";
+    case LQ_E_SIZE: return "incompatible size (StateInitializationError::IncompatibleSize)";
+    case LQ_E_CUDA: return "CUDA error";
+    case LQ_E_COMM: return "halo / all-reduce transport error (is lq_set_comm registered?)";
+    case LQ_E_ODD_EXTENT: return "checkerboard sweeps need even extents";
+    case LQ_E_GAUSS_DIVERGED: return "Gauss projection did not converge (GaussProjectionError)";
+    case LQ_E_ZERO_STEPS: return "zero integration steps (MultiIntegrationError::ZeroIntegration)";
+    case LQ_E_NOSNAPSHOT: return "no snapshot to restore";
+    case LQ_E_NODEVICE: return "no CUDA device (there is no CPU fallback)";
+    default: return "unknown error";
+  }
+}
+const char* lq_last_cuda_error(void) { return g_cuda_err; }
+int lq_version(void) { return 100; }
+int lq_device_count(int* n) {
+  if (!n) return LQ_E_BADARG;
+#ifdef LQ_HOST_EMU
+  *n = 1;
+#else
+  int k = 0;
+  if (cudaGetDeviceCount(&k) != cudaSuccess) k = 0;
+  *n = k;
+#endif
+  return LQ_OK;
+}
+
+int lq_ctx_create(lq_ctx** out, int device, int D, const int64_t* extent, double a, double beta, double CA) {
+  return ctx_create_common(out, device, D, extent, nullptr, nullptr, a, beta, CA);
+}
+int lq_ctx_create_dist(lq_ctx** out, int device, int D, const int64_t* gext, const int* proc_grid, const int* coord,
+                       double a, double beta, double CA) {
+  if (!proc_grid || !coord) return LQ_E_BADARG;
+  return ctx_create_common(out, device, D, gext, proc_grid, coord, a, beta, CA);
+}
+int lq_ctx_destroy(lq_ctx* c) {
+  if (!c) return LQ_OK;
+  LQ_GUARD(c);
+  rt_sync(c->stream);
+  rt_free(c->U);
+  rt_free(c->U2);
+  rt_free(c->E);
+  rt_free(c->E2);
+  rt_free(c->G);
+  rt_free(c->snapU);
+  rt_free(c->snapE);
+  rt_free(c->d_aos);
+  rt_free(c->d_partial);
+  rt_free(c->d_result);
+  rt_free_host(c->h_result);
+#ifndef LQ_HOST_EMU
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+#endif
+  delete c;
+  return LQ_OK;
+}
+int lq_set_flags(lq_ctx* c, int flags) {
+  if (!c) return LQ_E_BADARG;
+  c->flags = flags;
+  return LQ_OK;
+}
+int lq_get_flags(lq_ctx* c, int* flags) {
+  if (!c || !flags) return LQ_E_BADARG;
+  *flags = c->flags;
+  return LQ_OK;
+}
+int lq_set_beta(lq_ctx* c, double beta) {
+  if (!c) return LQ_E_BADARG;
+  c->beta = beta;
+  return LQ_OK;
+}
+int lq_sync(lq_ctx* c) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  return rt_sync(c->stream);
+}
+int lq_stream(lq_ctx* c, void** s) {
+  if (!c || !s) return LQ_E_BADARG;
+  *s = (void*)c->stream;
+  return LQ_OK;
+}
+int lq_set_stream(lq_ctx* c, void* s) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  LQ_TRY(rt_sync(c->stream));
+#ifndef LQ_HOST_EMU
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)s;
+#else
+  c->stream = s;
+#endif
+  c->own_stream = false;
+  return LQ_OK;
+}
+int64_t lq_num_sites(const lq_ctx* c) { return c ? c->g.vol : 0; }
+int64_t lq_num_links(const lq_ctx* c) { return c ? c->g.vol * c->g.D : 0; }
+int64_t lq_t(const lq_ctx* c) { return c ? c->t : 0; }
+int lq_set_t(lq_ctx* c, int64_t t) {
+  if (!c) return LQ_E_BADARG;
+  c->t = t;
+  return LQ_OK;
+}
+int64_t lq_kernel_launches(const lq_ctx* c) { return c ? c->launches : 0; }
+int lq_set_comm(lq_ctx* c, const lq_comm* comm) {
+  if (!c) return LQ_E_BADARG;
+  if (comm) {
+    c->comm = *comm;
+    c->has_comm = true;
+  } else {
+    c->has_comm = false;
+  }
+  return LQ_OK;
+}
+int lq_is_decomposed(const lq_ctx* c, int dir) { return (c && dir >= 0 && dir < c->g.D) ? c->g.ghost[dir] : 0; }
+
+// ---------------------------------------------------------------------------------------------- marshalling
+static int links_from_device_aos(lq_ctx* c, const double* d_aos) {
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinksFromAos<DD>{c->g, d_aos, c->U}))));
+  c->halo_ok[0] = false;
+  return LQ_OK;
+}
+static int efield_from_device_aos(lq_ctx* c, const double* d_aos) {
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KEFromAos<DD>{c->g, d_aos, c->E}))));
+  c->halo_ok[1] = false;
+  return LQ_OK;
+}
+static int links_to_device_aos(lq_ctx* c, double* d_aos) {
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinksToAos<DD>{c->g, c->U, d_aos}))));
+  return LQ_OK;
+}
+static int efield_to_device_aos(lq_ctx* c, double* d_aos) {
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KEToAos<DD>{c->g, c->E, d_aos}))));
+  return LQ_OK;
+}
+int lq_links_upload(lq_ctx* c, const double* aos, int64_t n_links) {
+  if (!c || !aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  size_t bytes = (size_t)n_links * 18 * sizeof(double);
+  LQ_TRY(ensure_aos(c, bytes));
+  LQ_TRY(rt_copy(c->d_aos, aos, bytes, H2D, c->stream));
+  LQ_TRY(links_from_device_aos(c, c->d_aos));
+  return rt_sync(c->stream);
+}
+int lq_links_download(lq_ctx* c, double* aos, int64_t n_links) {
+  if (!c || !aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  size_t bytes = (size_t)n_links * 18 * sizeof(double);
+  LQ_TRY(ensure_aos(c, bytes));
+  LQ_TRY(links_to_device_aos(c, c->d_aos));
+  LQ_TRY(rt_copy(aos, c->d_aos, bytes, D2H, c->stream));
+  return rt_sync(c->stream);
+}
+int lq_efield_upload(lq_ctx* c, const double* aos, int64_t n_links) {
+  if (!c || !aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  size_t bytes = (size_t)n_links * 8 * sizeof(double);
+  LQ_TRY(ensure_aos(c, bytes));
+  LQ_TRY(rt_copy(c->d_aos, aos, bytes, H2D, c->stream));
+  LQ_TRY(efield_from_device_aos(c, c->d_aos));
+  return rt_sync(c->stream);
+}
+int lq_efield_download(lq_ctx* c, double* aos, int64_t n_links) {
+  if (!c || !aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  size_t bytes = (size_t)n_links * 8 * sizeof(double);
+  LQ_TRY(ensure_aos(c, bytes));
+  LQ_TRY(efield_to_device_aos(c, c->d_aos));
+  LQ_TRY(rt_copy(aos, c->d_aos, bytes, D2H, c->stream));
+  return rt_sync(c->stream);
+}
+int lq_links_upload_device(lq_ctx* c, const double* d_aos, int64_t n_links) {
+  if (!c || !d_aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  return links_from_device_aos(c, d_aos);
+}
+int lq_links_download_device(lq_ctx* c, double* d_aos, int64_t n_links) {
+  if (!c || !d_aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  return links_to_device_aos(c, d_aos);
+}
+int lq_efield_upload_device(lq_ctx* c, const double* d_aos, int64_t n_links) {
+  if (!c || !d_aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  return efield_from_device_aos(c, d_aos);
+}
+int lq_efield_download_device(lq_ctx* c, double* d_aos, int64_t n_links) {
+  if (!c || !d_aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  return efield_to_device_aos(c, d_aos);
+}
+int lq_links_set_cold(lq_ctx* c) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinksCold<DD>{c->g, c->U}))));
+  c->halo_ok[0] = false;
+  return LQ_OK;
+}
+int lq_efield_set_zero(lq_ctx* c) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  c->halo_ok[1] = true;  // zero everywhere, ghosts included
+  return rt_memset(c->E, 0, c->e_bytes(), c->stream);
+}
+int lq_links_set_random(lq_ctx* c, uint64_t seed, uint64_t counter) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinksRandom<DD>{c->g, c->U, seed, counter}))));
+  c->halo_ok[0] = false;
+  return LQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- observables
+static int plaquette_all(lq_ctx* c, double v[3]) {
+  LQ_TRY(ensure_halo(c, 0));
+  LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol, KPlaquette<DD>{c->g, c->U, c->CA}))));
+  for (int k = 0; k < 3; ++k) v[k] = c->h_result[k];
+  return global_sum(c, v, 3);
+}
+int lq_plaquette_sum(lq_ctx* c, double out[2]) {
+  if (!c || !out) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  double v[3];
+  LQ_TRY(plaquette_all(c, v));
+  out[0] = v[0];
+  out[1] = v[1];
+  return LQ_OK;
+}
+int lq_average_trace_plaquette(lq_ctx* c, double out[2]) {
+  if (!c || !out) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  double v[3];
+  LQ_TRY(plaquette_all(c, v));
+  double npl = (double)(global_sites(c) * (c->g.D * (c->g.D - 1)) / 2);  // field.rs:801-803
+  out[0] = v[0] / npl;
+  out[1] = v[1] / npl;
+  return LQ_OK;
+}
+int lq_hamiltonian_links(lq_ctx* c, double* h) {
+  if (!c || !h) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  double v[3];
+  LQ_TRY(plaquette_all(c, v));
+  *h = v[2] * c->beta;
+  return LQ_OK;
+}
+int lq_hamiltonian_efield(lq_ctx* c, double* h) {
+  if (!c || !h) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol, KEfieldEnergy<DD>{c->g, c->E}))));
+  double v = c->h_result[0];
+  LQ_TRY(global_sum(c, &v, 1));
+  *h = v * c->beta;
+  return LQ_OK;
+}
+int lq_hamiltonian_total(lq_ctx* c, double* h) {
+  double a = 0, b = 0;
+  LQ_TRY(lq_hamiltonian_links(c, &a));
+  LQ_TRY(lq_hamiltonian_efield(c, &b));
+  *h = a + b;
+  return LQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- molecular dynamics
+static double force_coef(const lq_ctx* c) { return -sqrt(2.0 / c->CA) / c->a; }  // state.rs:1428
+static double link_coef(const lq_ctx* c) { return sqrt(2.0 * c->CA) / c->a; }    // state.rs:1412-1416
+
+int lq_staples(lq_ctx* c, double* aos_out, int64_t n_links) {
+  if (!c || !aos_out) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  size_t bytes = (size_t)n_links * 18 * sizeof(double);
+  LQ_TRY(ensure_aos(c, bytes));
+  LQ_TRY(ensure_halo(c, 0));
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KStaplesToAos<DD>{c->g, c->U, c->d_aos}))));
+  LQ_TRY(rt_copy(aos_out, c->d_aos, bytes, D2H, c->stream));
+  return rt_sync(c->stream);
+}
+int lq_force(lq_ctx* c, double* aos_out, int64_t n_links) {
+  if (!c || !aos_out) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  size_t bytes = (size_t)n_links * 8 * sizeof(double);
+  LQ_TRY(ensure_aos(c, bytes));
+  LQ_TRY(ensure_halo(c, 0));
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KForceToAos<DD>{c->g, c->U, c->d_aos, force_coef(c)}))));
+  LQ_TRY(rt_copy(aos_out, c->d_aos, bytes, D2H, c->stream));
+  return rt_sync(c->stream);
+}
+static int efield_step(lq_ctx* c, double dt, int nkick) {
+  LQ_TRY(ensure_halo(c, 0));
+#ifdef LQ_TUNED
+  if (c->g.D == 4) {
+    LQ_TRY(lq_tuned_efield_step(c->stream, c->g, c->U, c->E, force_coef(c), dt, nkick));
+    c->launches++;
+    c->halo_ok[1] = false;
+    return LQ_OK;
+  }
+#endif
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KEfieldStep<DD>{c->g, c->U, c->E, force_coef(c), dt, nkick}))));
+  c->halo_ok[1] = false;
+  return LQ_OK;
+}
+static int link_step(lq_ctx* c, const cx* Uin, cx* Uout, double dt, int use_exp) {
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinkStep<DD>{c->g, Uin, Uout, c->E, dt, link_coef(c), use_exp}))));
+  c->halo_ok[0] = false;
+  return LQ_OK;
+}
+// E += nkick * (dt_e F[U]);  U <- step(U, E_new, dt_u)  in one kernel (second link buffer, then swap)
+static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u) {
+  LQ_TRY(ensure_halo(c, 0));
+  LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
+#ifdef LQ_TUNED
+  if (c->g.D == 4) {
+    LQ_TRY(lq_tuned_efield_link_step(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u, link_coef(c), nkick));
+    c->launches++;
+  } else
+#endif
+  {
+    LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g),
+                                   KEfieldLinkStep<DD>{c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u, link_coef(c),
+                                                       nkick, 0}))));
+  }
+  cx* t = c->U;
+  c->U = c->U2;
+  c->U2 = t;
+  c->halo_ok[0] = false;
+  c->halo_ok[1] = false;
+  return LQ_OK;
+}
+int lq_efield_step(lq_ctx* c, double dt) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  return efield_step(c, dt, 1);
+}
+int lq_link_step(lq_ctx* c, double dt, int use_exp) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  return link_step(c, c->U, c->U, dt, use_exp);
+}
+int lq_integrate(lq_ctx* c, int kind, double dt) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  switch (kind) {
+    case LQ_SYNC_SYNC: {  // both from the old state, symplectic_euler_rayon.rs:127-143
+      LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
+      LQ_TRY(link_step(c, c->U, c->U2, dt, 0));
+      LQ_TRY(efield_step(c, dt, 1));  // still reads the old links in c->U
+      cx* t = c->U;
+      c->U = c->U2;
+      c->U2 = t;
+      c->halo_ok[0] = false;
+      c->t += 1;
+      return LQ_OK;
+    }
+    case LQ_LEAP_LEAP:  // :145-168
+      LQ_TRY(link_step(c, c->U, c->U, dt, 0));
+      LQ_TRY(efield_step(c, dt, 1));
+      c->t += 1;
+      return LQ_OK;
+    case LQ_SYNC_LEAP:  // :170-191 (t unchanged)
+      return efield_step(c, dt / 2.0, 1);
+    case LQ_LEAP_SYNC:  // :193-218
+      LQ_TRY(link_step(c, c->U, c->U, dt, 0));
+      LQ_TRY(efield_step(c, dt / 2.0, 1));
+      c->t += 1;
+      return LQ_OK;
+    case LQ_SYMPLECTIC:  // :220-252
+      LQ_TRY(efield_step(c, dt / 2.0, 1));
+      LQ_TRY(link_step(c, c->U, c->U, dt, 0));
+      LQ_TRY(efield_step(c, dt / 2.0, 1));
+      c->t += 1;
+      return LQ_OK;
+    default:
+      return LQ_E_BADARG;
+  }
+}
+int lq_symplectic_n(lq_ctx* c, double dt, int64_t n) {
+  if (!c) return LQ_E_BADARG;
+  if (n <= 0) return LQ_E_ZERO_STEPS;
+  LQ_GUARD(c);
+  if (c->flags & LQ_FLAG_NO_KICK_MERGE) {
+    for (int64_t k = 0; k < n; ++k) LQ_TRY(lq_integrate(c, LQ_SYMPLECTIC, dt));
+    return LQ_OK;
+  }
+  // n x [E(dt/2) U(dt) E(dt/2)]: the trailing kick of step k and the leading kick of step k+1 see the same links,
+  // so the force is evaluated once and applied twice (same rounding sequence); each kick is fused with the link
+  // step that follows it.
+  for (int64_t k = 0; k < n; ++k) LQ_TRY(efield_link_step(c, dt / 2.0, k == 0 ? 1 : 2, dt));
+  LQ_TRY(efield_step(c, dt / 2.0, 1));
+  c->t += n;
+  return LQ_OK;
+}
+int lq_leapfrog_n(lq_ctx* c, double dt, int64_t n) {
+  if (!c) return LQ_E_BADARG;
+  if (n <= 0) return LQ_E_ZERO_STEPS;
+  LQ_GUARD(c);
+  LQ_TRY(lq_integrate(c, LQ_SYNC_LEAP, dt));
+  for (int64_t k = 0; k + 1 < n; ++k) LQ_TRY(lq_integrate(c, LQ_LEAP_LEAP, dt));
+  return lq_integrate(c, LQ_LEAP_SYNC, dt);
+}
+int lq_reunitarize(lq_ctx* c) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KReunitarize<DD>{c->g, c->U}))));
+  c->halo_ok[0] = false;
+  return LQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- momenta + Gauss
+int lq_momenta_refresh(lq_ctx* c, uint64_t seed, uint64_t counter, double sigma) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KMomentaRefresh<DD>{c->g, c->E, seed, counter, sigma}))));
+  c->halo_ok[1] = false;
+  return LQ_OK;
+}
+static int gauss_field(lq_ctx* c) {
+  LQ_TRY(ensure_buf(&c->G, c->g_bytes(), c));
+  LQ_TRY(ensure_halo(c, 0));
+  LQ_TRY(ensure_halo(c, 1));
+  LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussField<DD>{c->g, c->U, c->E, c->G}))));
+  c->halo_ok[2] = false;
+  return LQ_OK;
+}
+int lq_gauss_field(lq_ctx* c, double* aos_out, int64_t n_sites) {
+  if (!c || !aos_out) return LQ_E_BADARG;
+  if (n_sites != c->g.vol) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  size_t bytes = (size_t)n_sites * 18 * sizeof(double);
+  LQ_TRY(ensure_aos(c, bytes));
+  LQ_TRY(gauss_field(c));
+  LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussToAos<DD>{c->g, c->G, c->d_aos}))));
+  LQ_TRY(rt_copy(aos_out, c->d_aos, bytes, D2H, c->stream));
+  return rt_sync(c->stream);
+}
+int lq_gauss_sum_div(lq_ctx* c, double* out) {
+  if (!c || !out) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  LQ_TRY(gauss_field(c));
+  LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol, KGaussDiv<DD>{c->g, c->G}))));
+  double v = c->h_result[0];
+  LQ_TRY(global_sum(c, &v, 1));
+  *out = v;
+  return LQ_OK;
+}
+int lq_gauss_project_step(lq_ctx* c) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  LQ_TRY(gauss_field(c));
+  LQ_TRY(ensure_halo(c, 2));
+  LQ_TRY(ensure_buf(&c->E2, c->e_bytes(), c));
+  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KGaussProjectStep<DD>{c->g, c->U, c->G, c->E, c->E2}))));
+  cx* t = c->E;
+  c->E = c->E2;
+  c->E2 = t;
+  c->halo_ok[1] = false;
+  return LQ_OK;
+}
+int lq_gauss_project(lq_ctx* c, int64_t max_steps, int64_t* steps_out) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  if (max_steps <= 0) max_steps = 1 << 20;
+  LQ_TRY(lq_gauss_project_step(c));
+  int64_t steps = 1;
+  const double thr = LQ_EPS * (double)(global_sites(c) * 4 * 8 * 10);  // field.rs:1285
+  for (;;) {
+    double v;
+    LQ_TRY(lq_gauss_sum_div(c, &v));
+    if (v != v) {
+      if (steps_out) *steps_out = steps;
+      return LQ_E_GAUSS_DIVERGED;
+    }
+    if (v <= thr) break;
+    if (steps >= max_steps) {
+      if (steps_out) *steps_out = steps;
+      return LQ_E_GAUSS_DIVERGED;
+    }
+    for (int k = 0; k < 4; ++k) {
+      LQ_TRY(lq_gauss_project_step(c));
+      ++steps;
+    }
+  }
+  if (steps_out) *steps_out = steps;
+  return LQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- sweeps
+int lq_sweep_heatbath(lq_ctx* c, uint64_t seed, uint64_t counter, double coupling_scale) {
+  if (!c) return LQ_E_BADARG;
+  if (!c->even_extents) return LQ_E_ODD_EXTENT;
+  LQ_GUARD(c);
+  for (int d = 0; d < c->g.D; ++d)
+    for (int p = 0; p < 2; ++p) {
+      LQ_TRY(ensure_halo(c, 0));
+      LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2,
+                                     KHeatBath<DD>{c->g, c->U, d, p, c->flags, c->beta * coupling_scale, seed, counter}))));
+      c->halo_ok[0] = false;
+    }
+  return LQ_OK;
+}
+int lq_sweep_overrelax(lq_ctx* c, int kind) {
+  if (!c || (kind != LQ_OR_ROTATION && kind != LQ_OR_REVERSE)) return LQ_E_BADARG;
+  if (!c->even_extents) return LQ_E_ODD_EXTENT;
+  LQ_GUARD(c);
+  for (int d = 0; d < c->g.D; ++d)
+    for (int p = 0; p < 2; ++p) {
+      LQ_TRY(ensure_halo(c, 0));
+      LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2, KOverrelax<DD>{c->g, c->U, d, p, kind}))));
+      c->halo_ok[0] = false;
+    }
+  return LQ_OK;
+}
+int lq_sweep_metropolis(lq_ctx* c, uint64_t seed, uint64_t counter, double spread, int n_update, int64_t* n_accept,
+                        double* sum_prob) {
+  if (!c || n_update < 1 || !(spread > 0.0 && spread < 1.0)) return LQ_E_BADARG;  // metropolis_hastings_sweep.rs:73-80
+  if (!c->even_extents) return LQ_E_ODD_EXTENT;
+  LQ_GUARD(c);
+  double acc[2] = {0.0, 0.0};
+  for (int d = 0; d < c->g.D; ++d)
+    for (int p = 0; p < 2; ++p) {
+      LQ_TRY(ensure_halo(c, 0));
+      LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol / 2,
+                                     KMetropolis<DD>{c->g, c->U, d, p, c->flags, n_update, c->beta, c->CA, spread, seed,
+                                                     counter}))));
+      acc[0] += c->h_result[0];
+      acc[1] += c->h_result[1];
+      c->halo_ok[0] = false;
+    }
+  LQ_TRY(global_sum(c, acc, 2));
+  if (n_accept) *n_accept = (int64_t)(acc[0] + 0.5);
+  if (sum_prob) *sum_prob = acc[1];
+  return LQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- HMC
+int lq_snapshot(lq_ctx* c) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  if (!c->snapU) LQ_TRY(rt_malloc((void**)&c->snapU, c->u_bytes()));
+  if (!c->snapE) LQ_TRY(rt_malloc((void**)&c->snapE, c->e_bytes()));
+  LQ_TRY(rt_copy(c->snapU, c->U, c->u_bytes(), D2D, c->stream));
+  LQ_TRY(rt_copy(c->snapE, c->E, c->e_bytes(), D2D, c->stream));
+  c->snap_t = c->t;
+  c->has_snap = true;
+  return LQ_OK;
+}
+int lq_restore(lq_ctx* c) {
+  if (!c) return LQ_E_BADARG;
+  if (!c->has_snap) return LQ_E_NOSNAPSHOT;
+  LQ_GUARD(c);
+  LQ_TRY(rt_copy(c->U, c->snapU, c->u_bytes(), D2D, c->stream));
+  LQ_TRY(rt_copy(c->E, c->snapE, c->e_bytes(), D2D, c->stream));
+  c->t = c->snap_t;
+  c->halo_ok[0] = c->halo_ok[1] = false;
+  return LQ_OK;
+}
+int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint64_t counter, double sigma,
+                      int use_current_e, int do_project, double* h_old, double* h_new, double* prob, int* accepted,
+                      int64_t* gauss_steps) {
+  if (!c) return LQ_E_BADARG;
+  if (n_steps <= 0) return LQ_E_ZERO_STEPS;
+  LQ_GUARD(c);
+  if (!use_current_e) LQ_TRY(lq_momenta_refresh(c, seed, counter, sigma));  // state.rs:1093-1099
+  int64_t gs = 0;
+  if (do_project) LQ_TRY(lq_gauss_project(c, 0, &gs));                      // state.rs:1100
+  if (gauss_steps) *gauss_steps = gs;
+  // keep the old links for the reject path (hybrid_monte_carlo.rs:603-611)
+  if (!c->snapU) LQ_TRY(rt_malloc((void**)&c->snapU, c->u_bytes()));
+  LQ_TRY(rt_copy(c->snapU, c->U, c->u_bytes(), D2D, c->stream));
+  int64_t t0 = c->t;
+  double h0, h1;
+  LQ_TRY(lq_hamiltonian_total(c, &h0));
+  LQ_TRY(lq_symplectic_n(c, dt, n_steps));  // hybrid_monte_carlo.rs:573-582
+  LQ_TRY(lq_hamiltonian_total(c, &h1));
+  double p = fmax(fmin(exp(h0 - h1), 1.0), 0.0);  // :584-589
+  LqStream acc(seed, counter, 0xFFFFFFFFFEull);
+  bool ok = acc.bernoulli(p);
+  if (!ok) {
+    LQ_TRY(rt_copy(c->U, c->snapU, c->u_bytes(), D2D, c->stream));
+    c->halo_ok[0] = false;
+    c->t = t0;
+  }
+  if (h_old) *h_old = h0;
+  if (h_new) *h_new = h1;
+  if (prob) *prob = p;
+  if (accepted) *accepted = ok ? 1 : 0;
+  return LQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- halos
+static int halo_field(lq_ctx* c, int which, cx** f, int* planes) {
+  switch (which) {
+    case 0: *f = c->U; *planes = 9 * c->g.D; return LQ_OK;
+    case 1: *f = c->E; *planes = 4 * c->g.D; return LQ_OK;
+    case 2: *f = c->G; *planes = 9; return c->G ? LQ_OK : LQ_E_BADARG;
+    default: return LQ_E_BADARG;
+  }
+}
+static lq_i64 face_sites(const lq_ctx* c, int dir) { return c->g.svol / c->g.sext[dir]; }
+int lq_halo_bytes(lq_ctx* c, int which, int dir, int64_t* bytes) {
+  if (!c || !bytes || dir < 0 || dir >= c->g.D || !c->g.ghost[dir]) return LQ_E_BADARG;
+  int planes = which == 0 ? 9 * c->g.D : which == 1 ? 4 * c->g.D : which == 2 ? 9 : -1;
+  if (planes < 0) return LQ_E_BADARG;
+  *bytes = (int64_t)(face_sites(c, dir) * planes * sizeof(cx));
+  return LQ_OK;
+}
+int lq_halo_pack(lq_ctx* c, int which, int dir, int side, void* d_buf, int64_t bytes) {
+  int64_t need;
+  LQ_TRY(lq_halo_bytes(c, which, dir, &need));
+  if (!d_buf || bytes != need || (side != 0 && side != 1)) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  cx* f;
+  int planes;
+  LQ_TRY(halo_field(c, which, &f, &planes));
+  lq_i64 nface = face_sites(c, dir);
+  int xh = side == 0 ? 1 : c->g.ext[dir];  // interior boundary slices
+  LQ_DISPATCH(c, LQ_TRY((launch(c, nface * planes, KHaloPack<DD>{c->g, f, (cx*)d_buf, dir, xh, planes, nface}))));
+  return LQ_OK;
+}
+int lq_halo_unpack(lq_ctx* c, int which, int dir, int side, const void* d_buf, int64_t bytes) {
+  int64_t need;
+  LQ_TRY(lq_halo_bytes(c, which, dir, &need));
+  if (!d_buf || bytes != need || (side != 0 && side != 1)) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  cx* f;
+  int planes;
+  LQ_TRY(halo_field(c, which, &f, &planes));
+  lq_i64 nface = face_sites(c, dir);
+  int xh = side == 0 ? 0 : c->g.ext[dir] + 1;  // ghost slices
+  LQ_DISPATCH(c, LQ_TRY((launch(c, nface * planes, KHaloUnpack<DD>{c->g, f, (const cx*)d_buf, dir, xh, planes, nface}))));
+  return LQ_OK;
+}
+int lq_halo_invalidate(lq_ctx* c, int which) {
+  if (!c || which < 0 || which > 2) return LQ_E_BADARG;
+  c->halo_ok[which] = false;
+  return LQ_OK;
+}
+
+}  // extern "C"

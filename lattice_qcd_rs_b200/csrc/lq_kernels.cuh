@@ -1,0 +1,608 @@
+// lq_kernels.cuh -- kernel bodies (one functor per kernel) of the pure-gauge SU(3) update path.
+// Each functor names the reference loop it replaces (file:line under /root/reference/src).
+// Thread mapping: whole-lattice kernels take i in [0, n_items) and decode (site, dir) themselves.
+#pragma once
+#include "lq_common.cuh"
+#include "lq_local.cuh"
+
+#define LQ_SITES_PER_GROUP 32  // per-link kernels: a block row = 32 consecutive sites x one direction (one warp)
+
+// i -> (site ordinal n, dir): groups of 32 sites x D dirs; lanes of a warp share `dir` and walk consecutive sites.
+template <int D>
+LQ_HD bool lq_decode_link(const LqGeom& g, lq_i64 i, lq_i64& n, int& dir) {
+  lq_i64 blk = i / (LQ_SITES_PER_GROUP * D);
+  int r = (int)(i - blk * (LQ_SITES_PER_GROUP * D));
+  dir = r / LQ_SITES_PER_GROUP;
+  n = blk * LQ_SITES_PER_GROUP + (r - dir * LQ_SITES_PER_GROUP);
+  return n < g.vol;
+}
+LQ_HD lq_i64 lq_link_items(const LqGeom& g) {
+  return ((g.vol + LQ_SITES_PER_GROUP - 1) / LQ_SITES_PER_GROUP) * LQ_SITES_PER_GROUP * g.D;
+}
+
+// AoS (reference) <-> M3: column-major (re, im) pairs, su3.rs:24-36 / 285-286
+LQ_HD M3 lq_m3_from_aos(const double* p) {
+  M3 r;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) r.e[3 * rr + c] = cmk(p[2 * (c * 3 + rr)], p[2 * (c * 3 + rr) + 1]);
+  return r;
+}
+LQ_HD void lq_m3_to_aos(double* p, const M3& m) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) {
+      p[2 * (c * 3 + rr)] = m.e[3 * rr + c].x;
+      p[2 * (c * 3 + rr) + 1] = m.e[3 * rr + c].y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- staples
+// Sum over the 2(D-1) staples around link (x, mu), already daggered the way both consumers need it:
+//   A(x,mu) = sum_{nu != mu} [ U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)  +  U_nu^+(x+mu-nu) U_mu^+(x-nu) U_nu(x-nu) ]
+// == `staple` of monte_carlo/mod.rs:339-362 == sum_d S_{mu,d}^+ of derivative_e (state.rs:1430-1438, with
+// sij of field.rs:743-758).
+template <int D>
+LQ_HD M3 lq_staple_sum(const cx* LQ_RESTRICT U, const LqGeom& g, const Site<D>& x, int mu) {
+  M3 acc = m3_zero();
+  Site<D> xpm = lq_up<D>(g, x, mu);
+#pragma unroll
+  for (int nu = 0; nu < D; ++nu) {
+    if (nu == mu) continue;
+    {  // up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)
+      Site<D> xpn = lq_up<D>(g, x, nu);
+      M3 a = lq_load_link(U, g, nu, lq_phys(g, xpm.s));
+      M3 b = lq_load_link(U, g, mu, lq_phys(g, xpn.s));
+      M3 t = m3_mul_nd(a, b);
+      M3 c = lq_load_link(U, g, nu, lq_phys(g, x.s));
+      m3_fma_nd(acc, t, c);
+    }
+    {  // down:  U_nu^+(x+mu-nu) U_mu^+(x-nu) U_nu(x-nu) = (U_mu(x-nu) U_nu(x+mu-nu))^+ U_nu(x-nu)
+      Site<D> xmn = lq_dn<D>(g, x, nu);
+      Site<D> xpmmn = lq_dn<D>(g, xpm, nu);
+      M3 a = lq_load_link(U, g, mu, lq_phys(g, xmn.s));
+      M3 b = lq_load_link(U, g, nu, lq_phys(g, xpmmn.s));
+      M3 t = m3_mul_nn(a, b);
+      M3 c = lq_load_link(U, g, nu, lq_phys(g, xmn.s));
+      m3_fma_dn(acc, t, c);
+    }
+  }
+  return acc;
+}
+// derivative_e for one link (state.rs:1420-1448):  F^a = -sqrt(2/CA)/a * Im Tr(T_a U_mu(x) A(x,mu))
+template <int D>
+LQ_HD A8 lq_force_link(const cx* LQ_RESTRICT U, const LqGeom& g, const Site<D>& x, int mu, double coef) {
+  M3 a = lq_staple_sum<D>(U, g, x, mu);
+  M3 u = lq_load_link(U, g, mu, lq_phys(g, x.s));
+  M3 w = m3_mul_nn(u, a);
+  cx tr[8];
+  lq_trace_gen(w, tr);
+  A8 f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f.e[k] = coef * tr[k].y;
+  return f;
+}
+
+// ---------------------------------------------------------------------------------------------- marshalling
+template <int D>
+struct KLinksFromAos {  // LatticeStateNew::new / set_link_matrix upload (state.rs:779-815)
+  LqGeom g;
+  const double* aos;
+  cx* U;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_i64 l = lq_local_index<D>(g, st);
+    lq_store_link(U, g, dir, lq_phys(g, st.s), lq_m3_from_aos(aos + (l * D + dir) * 18));
+  }
+};
+template <int D>
+struct KLinksToAos {
+  LqGeom g;
+  const cx* U;
+  double* aos;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_i64 l = lq_local_index<D>(g, st);
+    lq_m3_to_aos(aos + (l * D + dir) * 18, lq_load_link_rw(U, g, dir, lq_phys(g, st.s)));
+  }
+};
+template <int D>
+struct KEFromAos {
+  LqGeom g;
+  const double* aos;
+  cx* E;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_i64 l = lq_local_index<D>(g, st);
+    A8 a;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a.e[k] = aos[(l * D + dir) * 8 + k];
+    lq_store_e(E, g, dir, lq_phys(g, st.s), a);
+  }
+};
+template <int D>
+struct KEToAos {
+  LqGeom g;
+  const cx* E;
+  double* aos;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_i64 l = lq_local_index<D>(g, st);
+    A8 a = lq_load_e(E, g, dir, lq_phys(g, st.s));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) aos[(l * D + dir) * 8 + k] = a.e[k];
+  }
+};
+template <int D>
+struct KLinksCold {  // LatticeStateDefault::new_cold, state.rs:671-679
+  LqGeom g;
+  cx* U;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_store_link(U, g, dir, lq_phys(g, st.s), m3_ident());
+  }
+};
+template <int D>
+struct KLinksRandom {  // LinkMatrix::new_determinist, field.rs:646-659
+  LqGeom g;
+  cx* U;
+  uint64_t seed, counter;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    LqStream rng(seed, counter, (uint64_t)(lq_global_index<D>(g, st) * D + dir));
+    lq_store_link(U, g, dir, lq_phys(g, st.s), lq_random_su3(rng));
+  }
+};
+template <int D>
+struct KMomentaRefresh {  // EField::new_determinist with Normal(0, sigma), field.rs:1086-1099; state.rs:1097
+  LqGeom g;
+  cx* E;
+  uint64_t seed, counter;
+  double sigma;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    LqStream rng(seed, counter, (uint64_t)(lq_global_index<D>(g, st) * D + dir));
+    A8 a;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double z0, z1;
+      rng.normal_pair(z0, z1);
+      a.e[2 * k] = sigma * z0;
+      a.e[2 * k + 1] = sigma * z1;
+    }
+    lq_store_e(E, g, dir, lq_phys(g, st.s), a);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- observables
+// average_trace_plaquette (field.rs:775-804) and hamiltonian_links (state.rs:821-849) in one pass:
+//   v[0] += Re sum_{i<j} Tr P_ij(x); v[1] += Im ...; v[2] += sum_{i<j} (1 - Re Tr P_ij(x)/CA)
+// P_ij(x) = U_i(x) U_j(x+i) U_i^+(x+j) U_j^+(x)  (pij/sij, field.rs:743-771)
+template <int D>
+struct KPlaquette {
+  static constexpr int K = 3;
+  LqGeom g;
+  const cx* U;
+  double CA;
+  LQ_HD void operator()(lq_i64 n, double* v) const {
+    Site<D> x = lq_site<D>(g, n);
+    double sre = 0.0, sim = 0.0, sh = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      Site<D> xpi = lq_up<D>(g, x, i);
+#pragma unroll
+      for (int j = i + 1; j < D; ++j) {
+        Site<D> xpj = lq_up<D>(g, x, j);
+        M3 a = m3_mul_nn(lq_load_link(U, g, i, lq_phys(g, x.s)), lq_load_link(U, g, j, lq_phys(g, xpi.s)));
+        M3 b = m3_mul_nn(lq_load_link(U, g, j, lq_phys(g, x.s)), lq_load_link(U, g, i, lq_phys(g, xpj.s)));
+        cx t = m3_trace_nd(a, b);
+        sre += t.x;
+        sim += t.y;
+        sh += 1.0 - t.x / CA;
+      }
+    }
+    v[0] += sre;
+    v[1] += sim;
+    v[2] += sh;
+  }
+};
+// hamiltonian_efield (state.rs:1370-1385): sum_x sum_i trace_squared(E_i(x)) (field.rs:164-167); beta on the host
+template <int D>
+struct KEfieldEnergy {
+  static constexpr int K = 1;
+  LqGeom g;
+  const cx* E;
+  LQ_HD void operator()(lq_i64 n, double* v) const {
+    Site<D> x = lq_site<D>(g, n);
+    lq_i64 p = lq_phys(g, x.s);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      A8 a = lq_load_e(E, g, i, p);
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += a.e[k] * a.e[k];
+      s += t / 2.0;
+    }
+    v[0] += s;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- molecular dynamics
+template <int D>
+struct KStaplesToAos {  // staple(), monte_carlo/mod.rs:339-362 (parity / debug output)
+  LqGeom g;
+  const cx* U;
+  double* aos;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_i64 l = lq_local_index<D>(g, st);
+    lq_m3_to_aos(aos + (l * D + dir) * 18, lq_staple_sum<D>(U, g, st, dir));
+  }
+};
+template <int D>
+struct KForceToAos {  // derivative_e, state.rs:1420-1448
+  LqGeom g;
+  const cx* U;
+  double* aos;
+  double coef;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_i64 l = lq_local_index<D>(g, st);
+    A8 f = lq_force_link<D>(U, g, st, dir, coef);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) aos[(l * D + dir) * 8 + k] = f.e[k];
+  }
+};
+// integrate_efield over the lattice (integrator/mod.rs:240-254 under symplectic_euler_rayon.rs:88-104):
+// E <- E + F dt, applied `nkick` times with the same F (nkick = 2 merges the trailing dt/2 kick of one
+// symplectic step with the leading dt/2 kick of the next: same U, same F, same rounding sequence).
+template <int D>
+struct KEfieldStep {
+  LqGeom g;
+  const cx* U;
+  cx* E;
+  double coef, dt;
+  int nkick;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    A8 f = lq_force_link<D>(U, g, st, dir, coef);
+    lq_i64 p = lq_phys(g, st.s);
+    A8 e = lq_load_e(E, g, dir, p);
+    for (int kk = 0; kk < nkick; ++kk) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e.e[k] = fma(f.e[k], dt, e.e[k]);
+    }
+    lq_store_e(E, g, dir, p, e);
+  }
+};
+// integrate_link over the lattice (integrator/mod.rs:216-233 with derivative_u state.rs:1407-1417):
+//   Euler:  U <- U + dt * (E.to_matrix() U) * i sqrt(2 CA) / a        (the reference's rule)
+//   exp  :  U <- exp(i dt sqrt(2 CA)/a E^a T_a) U                     (optional, su3_exp_i su3.rs:832-855)
+template <int D>
+LQ_HD M3 lq_link_update(const M3& u, const A8& e, double dt, double c_u, int use_exp) {
+  if (use_exp) {
+    A8 s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s.e[k] = e.e[k] * (dt * c_u);
+    return m3_mul_nn(lq_su3_exp_i(s), u);
+  }
+  M3 eu = m3_mul_nn(lq_adjoint_to_matrix(e), u);
+  M3 r;
+  // (x + iy) * (i c) = -c y + i c x ; then * dt and added to U
+  double f = c_u * dt;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.e[k] = cmk(fma(-f, eu.e[k].y, u.e[k].x), fma(f, eu.e[k].x, u.e[k].y));
+  return r;
+}
+template <int D>
+struct KLinkStep {
+  LqGeom g;
+  const cx* Uin;
+  cx* Uout;
+  const cx* E;
+  double dt, c_u;  // c_u = sqrt(2 CA) / a
+  int use_exp;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_i64 p = lq_phys(g, st.s);
+    M3 u = lq_load_link_rw(Uin, g, dir, p);
+    A8 e = lq_load_e(E, g, dir, p);
+    lq_store_link(Uout, g, dir, p, lq_link_update<D>(u, e, dt, c_u, use_exp));
+  }
+};
+// Fused symplectic-Euler kernel: E(x,mu) += nkick * dt_e * F[U](x,mu);  Unew(x,mu) = step(U(x,mu), E_new, dt_u).
+// One pass reads U once (plus cached neighbours) and E once, writes E and the second link buffer.
+// Equivalent to KEfieldStep followed by KLinkStep (symplectic_euler_rayon.rs:222-252, first two stages).
+template <int D>
+struct KEfieldLinkStep {
+  LqGeom g;
+  const cx* U;
+  cx* Unew;
+  cx* E;
+  double coef, dt_e, dt_u, c_u;
+  int nkick, use_exp;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_i64 p = lq_phys(g, st.s);
+    M3 a = lq_staple_sum<D>(U, g, st, dir);
+    M3 u = lq_load_link(U, g, dir, p);
+    M3 w = m3_mul_nn(u, a);
+    cx tr[8];
+    lq_trace_gen(w, tr);
+    A8 e = lq_load_e(E, g, dir, p);
+    for (int kk = 0; kk < nkick; ++kk) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
+    }
+    lq_store_e(E, g, dir, p, e);
+    lq_store_link(Unew, g, dir, p, lq_link_update<D>(u, e, dt_u, c_u, use_exp));
+  }
+};
+template <int D>
+struct KReunitarize {  // LinkMatrix::normalize, field.rs:897-901 -> orthonormalize_matrix su3.rs:279-303
+  LqGeom g;
+  cx* U;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> st = lq_site<D>(g, n);
+    lq_i64 p = lq_phys(g, st.s);
+    lq_store_link(U, g, dir, p, lq_orthonormalize(lq_load_link_rw(U, g, dir, p)));
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- Gauss law
+// EField::gauss, field.rs:1174-1195:  G(x) = sum_i [ E_i(x) - U_i^+(x-i) E_i(x-i) U_i(x-i) ]
+template <int D>
+LQ_HD M3 lq_gauss_site(const cx* LQ_RESTRICT U, const cx* E, const LqGeom& g, const Site<D>& x) {
+  M3 acc = m3_zero();
+  lq_i64 p = lq_phys(g, x.s);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    acc = m3_add(acc, lq_adjoint_to_matrix(lq_load_e(E, g, i, p)));
+    Site<D> xm = lq_dn<D>(g, x, i);
+    lq_i64 pm = lq_phys(g, xm.s);
+    M3 u = lq_load_link(U, g, i, pm);
+    M3 em = lq_adjoint_to_matrix(lq_load_e(E, g, i, pm));
+    M3 t = m3_mul_dn(u, em);  // U^+ E
+    M3 neg = m3_zero();
+    m3_fma_nn(neg, t, u);
+    acc = m3_sub(acc, neg);
+  }
+  return acc;
+}
+// Writes G on every storage site whose backward neighbours are available: interior sites (needs the low E/U
+// ghosts) -- the high ghost layer of G needed by the projection step is exchanged / recomputed by the caller.
+template <int D>
+struct KGaussField {
+  LqGeom g;
+  const cx* U;
+  const cx* E;
+  cx* G;
+  LQ_HD void operator()(lq_i64 n) const {
+    Site<D> x = lq_site<D>(g, n);
+    M3 m = lq_gauss_site<D>(U, E, g, x);
+    lq_i64 p = lq_phys(g, x.s);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) G[k * g.pitch + p] = m.e[k];
+  }
+};
+template <int D>
+struct KGaussToAos {
+  LqGeom g;
+  const cx* G;
+  double* aos;
+  LQ_HD void operator()(lq_i64 n) const {
+    Site<D> x = lq_site<D>(g, n);
+    lq_i64 p = lq_phys(g, x.s);
+    M3 m;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m.e[k] = G[k * g.pitch + p];
+    lq_m3_to_aos(aos + lq_local_index<D>(g, x) * 18, m);
+  }
+};
+// gauss_sum_div, field.rs:1199-1220:  sum_x | Tr( (sum_a T_a) G(x) ) |
+template <int D>
+struct KGaussDiv {
+  static constexpr int K = 1;
+  LqGeom g;
+  const cx* G;
+  LQ_HD void operator()(lq_i64 n, double* v) const {
+    Site<D> x = lq_site<D>(g, n);
+    lq_i64 p = lq_phys(g, x.s);
+    M3 m;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m.e[k] = G[k * g.pitch + p];
+    cx tr[8];
+    lq_trace_gen(m, tr);
+    double re = 0.0, im = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      re += tr[k].x;
+      im += tr[k].y;
+    }
+    v[0] += sqrt(re * re + im * im);
+  }
+};
+// project_to_gauss_step, field.rs:1301-1337:
+//   E_i^a(x) <- 2 Re Tr( T_a [ (U_i(x) G(x) U_i^+(x) G(x+i) - G(x)) 0.12 + T_a E_i^a(x) ] )
+//             = 2 Re Tr(T_a M) + E_i^a(x)            (Tr T_a T_a = 1/2)
+template <int D>
+struct KGaussProjectStep {
+  LqGeom g;
+  const cx* U;
+  const cx* G;
+  const cx* Ein;
+  cx* Eout;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 n;
+    int dir;
+    if (!lq_decode_link<D>(g, i, n, dir)) return;
+    Site<D> x = lq_site<D>(g, n);
+    lq_i64 p = lq_phys(g, x.s);
+    Site<D> xp = lq_up<D>(g, x, dir);
+    lq_i64 pp = lq_phys(g, xp.s);
+    M3 u = lq_load_link(U, g, dir, p);
+    M3 gx, gp;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      gx.e[k] = G[k * g.pitch + p];
+      gp.e[k] = G[k * g.pitch + pp];
+    }
+    M3 t = m3_mul_nd(m3_mul_nn(u, gx), u);
+    M3 m = m3_mul_nn(t, gp);
+    m = m3_scale(m3_sub(m, gx), 0.12);
+    cx tr[8];
+    lq_trace_gen(m, tr);
+    A8 e = lq_load_e(Ein, g, dir, p);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e.e[k] = 2.0 * (tr[k].x + 0.5 * e.e[k]);
+    lq_store_e(Eout, g, dir, p, e);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- checkerboard sweeps
+// One launch per (dir, colour): the links (x, dir) with colour(x) = parity do not enter each other's staples,
+// so the parallel update equals the serial loop over them (heat_bath.rs:113-123 visits links one by one).
+template <int D>
+struct KHeatBath {  // HeatBathSweep, heat_bath.rs:73-123
+  LqGeom g;
+  cx* U;
+  int dir, parity, flags;
+  double coupling;  // beta * coupling_scale
+  uint64_t seed, counter;
+  LQ_HD void operator()(lq_i64 n) const {
+    Site<D> x = lq_site_eo<D>(g, n, parity);
+    lq_i64 p = lq_phys(g, x.s);
+    M3 a = lq_staple_sum<D>(U, g, x, dir);
+    M3 u = lq_load_link_rw(U, g, dir, p);
+    LqStream rng(seed, counter, (uint64_t)(lq_global_index<D>(g, x) * D + dir));
+    lq_store_link(U, g, dir, p, lq_heat_bath_link(u, a, coupling, rng, flags));
+  }
+};
+template <int D>
+struct KOverrelax {  // OverrelaxationSweep{Rotation,Reverse}, overrelaxation.rs:86-110, 158-184
+  LqGeom g;
+  cx* U;
+  int dir, parity, kind;
+  LQ_HD void operator()(lq_i64 n) const {
+    Site<D> x = lq_site_eo<D>(g, n, parity);
+    lq_i64 p = lq_phys(g, x.s);
+    M3 a = lq_staple_sum<D>(U, g, x, dir);
+    M3 u = lq_load_link_rw(U, g, dir, p);
+    lq_store_link(U, g, dir, p, lq_overrelax_link(u, a, kind));
+  }
+};
+template <int D>
+struct KMetropolis {  // MetropolisHastingsSweep, metropolis_hastings_sweep.rs:126-174; v = (#accepted, sum prob)
+  static constexpr int K = 2;
+  LqGeom g;
+  cx* U;
+  int dir, parity, flags, n_update;
+  double beta, CA, spread;
+  uint64_t seed, counter;
+  LQ_HD void operator()(lq_i64 n, double* v) const {
+    Site<D> x = lq_site_eo<D>(g, n, parity);
+    lq_i64 p = lq_phys(g, x.s);
+    M3 old = lq_load_link_rw(U, g, dir, p);
+    LqStream rng(seed, counter, (uint64_t)(lq_global_index<D>(g, x) * D + dir));
+    M3 prop = lq_metropolis_proposal(old, n_update, spread, rng, flags);
+    M3 a = lq_staple_sum<D>(U, g, x, dir);
+    double proba = fmax(fmin(exp(-lq_delta_s(a, prop, old, beta, CA)), 1.0), 0.0);
+    v[1] += proba;
+    if (rng.bernoulli(proba)) {
+      v[0] += 1.0;
+      lq_store_link(U, g, dir, p, prop);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- halos
+// Face slices of a decomposed direction `hd`: n in [0, face sites) enumerates storage sites with x[hd] fixed
+// (all other directions over their full STORAGE extent, so later directions carry earlier ghosts = corners).
+template <int D>
+LQ_HD lq_i64 lq_face_site(const LqGeom& g, int hd, int xh, lq_i64 n) {
+  lq_i64 s = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    int xd;
+    if (d == hd) {
+      xd = xh;
+    } else {
+      lq_i64 q = n / g.sext[d];
+      xd = (int)(n - q * g.sext[d]);
+      n = q;
+    }
+    s += (lq_i64)xd * g.sstride[d];
+  }
+  return s;
+}
+// planes = 9*D (links) or 4*D (efield); buffer layout [plane][face site]
+template <int D>
+struct KHaloPack {
+  LqGeom g;
+  const cx* F;
+  cx* buf;
+  int hd, xh, planes;
+  lq_i64 nface;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 pl = i / nface;
+    lq_i64 n = i - pl * nface;
+    if (pl >= planes) return;
+    buf[i] = F[pl * g.pitch + lq_phys(g, lq_face_site<D>(g, hd, xh, n))];
+  }
+};
+template <int D>
+struct KHaloUnpack {
+  LqGeom g;
+  cx* F;
+  const cx* buf;
+  int hd, xh, planes;
+  lq_i64 nface;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 pl = i / nface;
+    lq_i64 n = i - pl * nface;
+    if (pl >= planes) return;
+    F[pl * g.pitch + lq_phys(g, lq_face_site<D>(g, hd, xh, n))] = buf[i];
+  }
+};

@@ -1,0 +1,351 @@
+// lq_local.cuh -- counter-based RNG and the single-link update rules of the local sweeps
+// (heat bath, over-relaxation, Metropolis).  All host/device inline; one thread updates one link.
+#pragma once
+#include "lq_common.cuh"
+
+// ---------------------------------------------------------------------------------------------- Philox4x32-10
+// Salmon et al. SC'11.  One stream per (seed, call counter, global link index); 53-bit uniforms, two per block.
+// (The reference draws from rand 0.8 StdRng, an un-vendored dependency whose stream no reference test pins;
+//  the library and the oracle share this specified generator instead.)
+struct LqStream {
+  uint32_t key[2], ctr[4], buf[4];
+  int have;
+  LQ_HD LqStream(uint64_t seed, uint64_t counter, uint64_t idx) {
+    key[0] = (uint32_t)seed;
+    key[1] = (uint32_t)(seed >> 32);
+    ctr[0] = 0;
+    ctr[1] = (uint32_t)idx;
+    ctr[2] = (uint32_t)counter;
+    ctr[3] = ((uint32_t)(counter >> 32) & 0x00FFFFFFu) | (((uint32_t)(idx >> 32) & 0xFFu) << 24);
+    have = 0;
+    buf[0] = buf[1] = buf[2] = buf[3] = 0;
+  }
+  LQ_HD void block() {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+      uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+      uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+      uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+      c1 = (uint32_t)p1;
+      c3 = (uint32_t)p0;
+      c0 = n0;
+      c2 = n2;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    buf[0] = c0;
+    buf[1] = c1;
+    buf[2] = c2;
+    buf[3] = c3;
+  }
+  LQ_HD uint64_t bits53() {
+    if (have == 0) {
+      block();
+      ctr[0] += 1;
+      have = 2;
+    }
+    int o = (2 - have) * 2;
+    --have;
+    uint32_t hi = o == 0 ? buf[0] : buf[2];
+    uint32_t lo = o == 0 ? buf[1] : buf[3];
+    return ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+  }
+  LQ_HD double uniform01() { return (double)bits53() * 0x1.0p-53; }            // [0,1)
+  LQ_HD double open_closed01() { return (double)(bits53() + 1) * 0x1.0p-53; }  // (0,1]
+  LQ_HD double uniform_pm1() { return 2.0 * uniform01() - 1.0; }              // [-1,1)
+  LQ_HD bool bernoulli(double p) { return uniform01() < p; }
+  LQ_HD void normal_pair(double& z0, double& z1) {  // Box-Muller from one Philox block
+    double u1 = open_closed01();
+    double u2 = uniform01();
+    double r = sqrt(-2.0 * log(u1));
+    double th = 2.0 * LQ_PI * u2;
+    z0 = r * cos(th);
+    z1 = r * sin(th);
+  }
+};
+
+#define LQ_KP_MAX_ITER 10000 /* the reference loops forever on NaN parameters; cap and return x0 = 1 */
+
+// ---------------------------------------------------------------------------------------------- 2x2
+struct M2 {
+  cx a, b, c, d;  // [[a, b], [c, d]]
+};
+LQ_HD M2 m2_mul(const M2& x, const M2& y) {
+  M2 r;
+  r.a = cadd(cmul(x.a, y.a), cmul(x.b, y.c));
+  r.b = cadd(cmul(x.a, y.b), cmul(x.b, y.d));
+  r.c = cadd(cmul(x.c, y.a), cmul(x.d, y.c));
+  r.d = cadd(cmul(x.c, y.b), cmul(x.d, y.d));
+  return r;
+}
+LQ_HD M2 m2_adj(const M2& x) {
+  M2 r;
+  r.a = cconj(x.a);
+  r.b = cconj(x.c);
+  r.c = cconj(x.b);
+  r.d = cconj(x.d);
+  return r;
+}
+LQ_HD cx m2_det(const M2& x) { return csub(cmul(x.a, x.d), cmul(x.c, x.b)); }
+LQ_HD bool lq_is_normal(double v) { return isfinite(v) && fabs(v) >= DBL_MIN; }
+
+// complex_matrix_from_vec, su2.rs:134-140 -- PAULI_3 as coded is diag(1,1) (su2.rs:39-45) unless the
+// context carries LQ_FLAG_PAULI3_FIXED (bit 0).
+LQ_HD M2 lq_matrix_from_vec(double x0, const double x[3], int flags) {
+  M2 r;
+  r.a = cmk(x0, x[2]);
+  r.b = cmk(x[1], x[0]);
+  r.c = cmk(-x[1], x[0]);
+  r.d = (flags & 1) ? cmk(x0, -x[2]) : cmk(x0, x[2]);
+  return r;
+}
+// random_su2_close_to_unity, su2.rs:80-100
+LQ_HD M2 lq_random_su2_close_to_unity(double spread, LqStream& rng, int flags) {
+  double r[3];
+  r[0] = rng.uniform_pm1();
+  r[1] = rng.uniform_pm1();
+  r[2] = rng.uniform_pm1();
+  double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  double x[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) x[k] = (n > LQ_EPS ? r[k] / n : r[k]) * spread;
+  double x0u = sqrt(1.0 - (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]));
+  double x0 = rng.bernoulli(0.5) ? x0u : -x0u;
+  return lq_matrix_from_vec(x0, x, flags);
+}
+// get_r / get_s / get_t (su3.rs:428-530): embed a 2x2 block into rows/cols (0,1), (0,2), (1,2)
+LQ_HD M3 lq_embed(const M2& m, int which) {
+  const int ia = which == 2 ? 1 : 0;
+  const int ib = which == 0 ? 1 : 2;
+  M3 r = m3_ident();
+  r.e[3 * ia + ia] = m.a;
+  r.e[3 * ia + ib] = m.b;
+  r.e[3 * ib + ia] = m.c;
+  r.e[3 * ib + ib] = m.d;
+  return r;
+}
+// get_sub_block_{r,s,t}, su3.rs:559-620
+LQ_HD M2 lq_sub_block(const M3& m, int which) {
+  const int ia = which == 2 ? 1 : 0;
+  const int ib = which == 0 ? 1 : 2;
+  M2 r;
+  r.a = m.e[3 * ia + ia];
+  r.b = m.e[3 * ia + ib];
+  r.c = m.e[3 * ib + ia];
+  r.d = m.e[3 * ib + ib];
+  return r;
+}
+// project_to_su2_unorm, su2.rs:155-157:  m - m^dagger + 1 * conj(tr m)
+LQ_HD M2 lq_project_to_su2_unorm(const M2& m) {
+  M2 ad = m2_adj(m), r;
+  cx t = cconj(cadd(m.a, m.d));
+  r.a = cadd(csub(m.a, ad.a), t);
+  r.b = csub(m.b, ad.b);
+  r.c = csub(m.c, ad.c);
+  r.d = cadd(csub(m.d, ad.d), t);
+  return r;
+}
+// random_su3_close_to_unity, su3.rs:385-398
+LQ_HD M3 lq_random_su3_close_to_unity(double spread, LqStream& rng, int flags) {
+  M3 r = lq_embed(lq_random_su2_close_to_unity(spread, rng, flags), 0);
+  M3 s = lq_embed(lq_random_su2_close_to_unity(spread, rng, flags), 1);
+  M3 t = lq_embed(lq_random_su2_close_to_unity(spread, rng, flags), 2);
+  M3 x = m3_mul_nn(m3_mul_nn(r, s), t);
+  if (rng.bernoulli(0.5)) x = m3_adj(x);
+  return x;
+}
+// random_su3, su3.rs:322-355 (Gram-Schmidt of two Uniform(-1,1)^6 vectors)
+LQ_HD M3 lq_random_su3(LqStream& rng) {
+  cx v1[3], v2[3];
+  int guard = 0;
+  do {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double re = rng.uniform_pm1();
+      double im = rng.uniform_pm1();
+      v1[k] = cmk(re, im);
+    }
+  } while (sqrt(cnorm2(v1[0]) + cnorm2(v1[1]) + cnorm2(v1[2])) <= LQ_EPS && ++guard < LQ_KP_MAX_ITER);
+  guard = 0;
+  cx dot;
+  do {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double re = rng.uniform_pm1();
+      double im = rng.uniform_pm1();
+      v2[k] = cmk(re, im);
+    }
+    dot = cadd(cadd(cmul(v1[0], v2[0]), cmul(v1[1], v2[1])), cmul(v1[2], v2[2]));  // non-conjugating, su3.rs:343
+  } while (sqrt(cnorm2(dot)) <= LQ_EPS && ++guard < LQ_KP_MAX_ITER);
+  M3 m = m3_zero();
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    m.e[3 * k + 0] = v1[k];
+    m.e[3 * k + 1] = v2[k];
+  }
+  return lq_orthonormalize(m);
+}
+// random_su2, su2.rs:200-216
+LQ_HD M2 lq_random_su2(LqStream& rng) {
+  cx v0, v1;
+  double n;
+  int guard = 0;
+  do {
+    double re = rng.uniform_pm1();
+    double im = rng.uniform_pm1();
+    v0 = cmk(re, im);
+    re = rng.uniform_pm1();
+    im = rng.uniform_pm1();
+    v1 = cmk(re, im);
+    n = sqrt(cnorm2(v0) + cnorm2(v1));
+  } while (!lq_is_normal(n) && ++guard < LQ_KP_MAX_ITER);
+  cx a = cmk(v0.x / n, v0.y / n), b = cmk(v1.x / n, v1.y / n);
+  M2 r;
+  r.a = a;
+  r.b = b;
+  r.c = cneg(cconj(b));
+  r.d = cconj(a);
+  return r;
+}
+// ModifiedNormal + HeatBathDistributionNorm (Kennedy-Pendleton), distribution.rs:89-100, 336-350
+LQ_HD double lq_heat_bath_norm(double param_exp, LqStream& rng) {
+  for (int it = 0; it < LQ_KP_MAX_ITER; ++it) {
+    double r = rng.uniform01();
+    double r0 = rng.open_closed01();
+    double r1 = rng.open_closed01();
+    double r2 = rng.open_closed01();
+    double c = cos(2.0 * LQ_PI * r1);
+    double lambda = sqrt(-(log(r0) + c * c * log(r2)) / (2.0 * param_exp));
+    if (r * r <= 1.0 - lambda * lambda) return 1.0 - 2.0 * (lambda * lambda);
+  }
+  return 1.0;
+}
+// HeatBathDistribution -> 2x2 matrix, distribution.rs:199-219 (direction = normalised cube sample, as coded)
+LQ_HD M2 lq_heat_bath_matrix(double param_exp, LqStream& rng, int flags) {
+  double x0 = lq_heat_bath_norm(param_exp, rng);
+  double xu[3], n;
+  int guard = 0;
+  do {
+    xu[0] = rng.uniform_pm1();
+    xu[1] = rng.uniform_pm1();
+    xu[2] = rng.uniform_pm1();
+    n = sqrt(xu[0] * xu[0] + xu[1] * xu[1] + xu[2] * xu[2]);
+  } while (n <= LQ_EPS && ++guard < LQ_KP_MAX_ITER);
+  double sc = sqrt(1.0 - x0 * x0);
+  double x[3] = {xu[0] / n * sc, xu[1] / n * sc, xu[2] / n * sc};
+  return lq_matrix_from_vec(x0, x, flags);
+}
+// heat_bath_su2, heat_bath.rs:73-86.  coupling = beta * coupling_scale (reference: scale 1, i.e. beta*k).
+LQ_HD M2 lq_heat_bath_su2(const M2& stap, double coupling, LqStream& rng, int flags) {
+  double k = sqrt(m2_det(stap).x);
+  if (lq_is_normal(k)) {
+    M2 v = m2_adj(stap);
+    v.a = cmk(v.a.x / k, v.a.y / k);
+    v.b = cmk(v.b.x / k, v.b.y / k);
+    v.c = cmk(v.c.x / k, v.c.y / k);
+    v.d = cmk(v.d.x / k, v.d.y / k);
+    M2 x = lq_heat_bath_matrix(coupling * k, rng, flags);
+    return m2_mul(x, v);
+  }
+  return lq_random_su2(rng);
+}
+// HeatBathSweep::get_modif, heat_bath.rs:90-109: Cabibbo-Marinari over the r, s, t SU(2) blocks.
+LQ_HD M3 lq_heat_bath_link(const M3& u, const M3& a, double coupling, LqStream& rng, int flags) {
+  M3 w = m3_mul_nn(u, a);
+  M3 r = lq_embed(lq_heat_bath_su2(lq_project_to_su2_unorm(lq_sub_block(w, 0)), coupling, rng, flags), 0);
+  M3 ru = m3_mul_nn(r, u);
+  w = m3_mul_nn(ru, a);
+  M3 s = lq_embed(lq_heat_bath_su2(lq_project_to_su2_unorm(lq_sub_block(w, 1)), coupling, rng, flags), 1);
+  M3 sru = m3_mul_nn(s, ru);
+  w = m3_mul_nn(sru, a);
+  M3 t = lq_embed(lq_heat_bath_su2(lq_project_to_su2_unorm(lq_sub_block(w, 2)), coupling, rng, flags), 2);
+  return m3_mul_nn(t, sru);
+}
+// MetropolisHastingsSweep::potential_modif, metropolis_hastings_sweep.rs:126-143
+LQ_HD M3 lq_metropolis_proposal(const M3& old_link, int n_update, double spread, LqStream& rng, int flags) {
+  M3 nl = old_link;
+  for (int k = 0; k < n_update; ++k) {
+    M3 rm = lq_orthonormalize(lq_random_su3_close_to_unity(spread, rng, flags));
+    nl = m3_mul_nn(rm, nl);
+  }
+  return nl;
+}
+// delta_s_old_new_cmp, monte_carlo/mod.rs:324-334:  -Re Tr((U' - U) A) beta / CA
+LQ_HD double lq_delta_s(const M3& stap, const M3& nl, const M3& ol, double beta, double CA) {
+  M3 d = m3_sub(nl, ol);
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tr += d.e[3 * i + k].x * stap.e[3 * k + i].x - d.e[3 * i + k].y * stap.e[3 * k + i].y;
+  return -tr * beta / CA;
+}
+
+// ---------------------------------------------------------------------------------------------- 3x3 SVD
+// nalgebra SVD::new(a, true, true) (overrelaxation.rs:95, 167) is an un-vendored dependency; the over-relaxation
+// results do not depend on the SVD convention for non-degenerate singular values, so an accurate one-sided
+// Jacobi (Hestenes) serves:  a = u diag(s) v^dagger.
+LQ_HD void lq_svd3(const M3& a, M3& u, M3& v) {
+  M3 w = a;
+  v = m3_ident();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double app = 0.0, aqq = 0.0;
+        cx apq = cmk(0.0, 0.0);
+        for (int k = 0; k < 3; ++k) {
+          app += cnorm2(w.e[3 * k + p]);
+          aqq += cnorm2(w.e[3 * k + q]);
+          apq = cadd(apq, cmul(cconj(w.e[3 * k + p]), w.e[3 * k + q]));
+        }
+        double gg = sqrt(cnorm2(apq));
+        if (gg <= 1e-300 || gg <= 1e-17 * sqrt(app * aqq)) continue;
+        off = fmax(off, gg / sqrt(app * aqq));
+        cx ph = cmk(apq.x / gg, apq.y / gg);
+        double zeta = (aqq - app) / (2.0 * gg);
+        double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        cx phc_sn = cscale(cconj(ph), sn), ph_sn = cscale(ph, sn);
+        for (int k = 0; k < 3; ++k) {
+          cx wp = w.e[3 * k + p], wq = w.e[3 * k + q];
+          w.e[3 * k + p] = csub(cscale(wp, c), cmul(wq, phc_sn));
+          w.e[3 * k + q] = cadd(cmul(wp, ph_sn), cscale(wq, c));
+          cx vp = v.e[3 * k + p], vq = v.e[3 * k + q];
+          v.e[3 * k + p] = csub(cscale(vp, c), cmul(vq, phc_sn));
+          v.e[3 * k + q] = cadd(cmul(vp, ph_sn), cscale(vq, c));
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  u = m3_zero();
+  for (int j = 0; j < 3; ++j) {
+    double n = 0.0;
+    for (int k = 0; k < 3; ++k) n += cnorm2(w.e[3 * k + j]);
+    n = sqrt(n);
+    for (int k = 0; k < 3; ++k)
+      u.e[3 * k + j] = (n > 0.0) ? cmk(w.e[3 * k + j].x / n, w.e[3 * k + j].y / n) : cmk(k == j ? 1.0 : 0.0, 0.0);
+  }
+}
+// su3::reverse, su3.rs:705-714: negate the off-diagonal entries
+LQ_HD M3 lq_reverse(const M3& a) {
+  M3 r;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.e[k] = (k == 0 || k == 4 || k == 8) ? a.e[k] : cneg(a.e[k]);
+  return r;
+}
+// OverrelaxationSweepRotation::get_modif, overrelaxation.rs:86-98:  rot U^dagger rot,  rot = u v^dagger of svd(A^dagger)
+// OverrelaxationSweepReverse::get_modif, overrelaxation.rs:158-171: u reverse(u^dagger U v) v^dagger
+LQ_HD M3 lq_overrelax_link(const M3& ulink, const M3& stap, int kind) {
+  M3 u, v;
+  lq_svd3(m3_adj(stap), u, v);
+  if (kind == 0) {
+    M3 rot = m3_mul_nd(u, v);
+    return m3_mul_nn(m3_mul_nd(rot, ulink), rot);
+  }
+  M3 inner = m3_mul_nn(m3_mul_dn(u, ulink), v);
+  return m3_mul_nd(m3_mul_nn(u, lq_reverse(inner)), v);
+}

@@ -1,0 +1,353 @@
+"""Parity of the kernel path with the CPU oracle, through the C ABI (include/lqcd_b200.h).
+
+Every test runs on two backends:
+  * "cuda" (marked gpu): the product library lattice_qcd_rs_b200/liblqcd_b200.so on the B200;
+  * "emu"  (CPU CI)    : the same kernel bodies compiled for the host (tests/emu.py, test infrastructure).
+Tolerances: deterministic paths <= 1e-12 relative (north_star); per-link stochastic updates share the oracle's
+Philox streams, so they are compared element-wise too (1e-9: a handful of libm calls sit between the streams
+and the links).
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from tests.conftest import SEED_RNG
+
+RTOL = 1e-12
+
+
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request):
+    if request.param == "emu":
+        from tests import emu
+        return emu.context
+    import torch
+    assert torch.cuda.is_available(), "the gpu-marked tests need a CUDA device (no CPU fallback)"
+    from lattice_qcd_rs_b200 import Context
+    return Context
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def hot(o, seed=SEED_RNG):
+    return o.links_random(seed)
+
+
+CASES = [(4, [4, 4, 4, 4]), (4, [8, 8, 8, 8]), (3, [6, 6, 6]), (2, [8, 8]), (4, [4, 6, 2, 8]), (4, [5, 5, 5, 5]),
+         (3, [3, 4, 5])]
+
+
+@pytest.mark.parametrize("D,ext", CASES)
+def test_roundtrip_and_observables(backend, D, ext):
+    o = Oracle(D, ext, a=1.3, beta=6.0)
+    c = backend(D, ext, a=1.3, beta=6.0)
+    U = hot(o)
+    E = o.momenta_refresh(SEED_RNG, 1)
+    c.links_upload(U)
+    c.efield_upload(E)
+    assert np.array_equal(c.links_download(), U)
+    assert np.array_equal(c.efield_download(), E)
+    ps, po = c.plaquette_sum(), o.plaquette_sum(U)
+    assert abs(ps - po) <= RTOL * abs(po)
+    assert abs(c.average_trace_plaquette() - o.average_trace_plaquette(U)) <= RTOL * abs(po)
+    assert abs(c.hamiltonian_links() - o.hamiltonian_links(U)) <= RTOL * abs(o.hamiltonian_links(U))
+    assert abs(c.hamiltonian_efield() - o.hamiltonian_efield(E)) <= RTOL * abs(o.hamiltonian_efield(E))
+    assert abs(c.hamiltonian_total() - o.hamiltonian_total(U, E)) <= RTOL * abs(o.hamiltonian_total(U, E))
+
+
+def test_errors(backend):
+    from lattice_qcd_rs_b200 import LqError
+    c = backend(4, 4)
+    with pytest.raises(LqError) as e:  # StateInitializationError::IncompatibleSize, state.rs:784-786
+        c.links_upload(np.zeros((c.nl - 1, 18)))
+    assert e.value.name == "LQ_E_SIZE"
+    with pytest.raises(LqError) as e:
+        c.efield_upload(np.zeros((c.nl + 4, 8)))
+    assert e.value.name == "LQ_E_SIZE"
+    with pytest.raises(LqError) as e:  # LatticeCyclic::new: dim >= 2 (lattice.rs:190-201)
+        backend(4, [4, 4, 1, 4])
+    assert e.value.name == "LQ_E_BADARG"
+    with pytest.raises(LqError):
+        backend(5, [4] * 5)
+    with pytest.raises(LqError) as e:  # MultiIntegrationError::ZeroIntegration, state.rs:480-482
+        c.symplectic_n(0.1, 0)
+    assert e.value.name == "LQ_E_ZERO_STEPS"
+    with pytest.raises(LqError) as e:
+        c.restore()
+    assert e.value.name == "LQ_E_NOSNAPSHOT"
+    odd = backend(4, [5, 4, 4, 4])
+    odd.links_set_cold()
+    with pytest.raises(LqError) as e:
+        odd.sweep_heatbath(1, 0)
+    assert e.value.name == "LQ_E_ODD_EXTENT"
+    with pytest.raises(LqError):  # spread must be in (0,1): metropolis_hastings_sweep.rs:73-80
+        c.sweep_metropolis(1, 0, spread=1.5)
+
+
+def test_cold_start_exact(backend):
+    """test_sim_cold (test/mod.rs:431-453): U = 1, E = 0 is an exact fixed point of every composition."""
+    c = backend(4, 4, a=1.0, beta=1.0)
+    o = Oracle(4, 4)
+    c.links_set_cold()
+    c.efield_set_zero()
+    assert np.array_equal(c.links_download(), o.cold_links())
+    for kind in (2, 1, 3, 0, 4):
+        c.integrate(kind, 0.1)
+    c.symplectic_n(0.1, 3)
+    c.leapfrog_n(0.1, 3)
+    assert np.array_equal(c.links_download(), o.cold_links())
+    assert np.array_equal(c.efield_download(), o.cold_efield())
+    assert c.plaquette_sum() == complex(3.0 * 6 * 256, 0.0)
+    assert c.hamiltonian_links() == 0.0 and c.hamiltonian_efield() == 0.0
+    assert c.t == 4 + 3 + 3  # sync_leap does not advance t (symplectic_euler_rayon.rs:170-191)
+
+
+@pytest.mark.parametrize("D,ext", CASES)
+def test_staples_and_force(backend, D, ext):
+    o = Oracle(D, ext, a=0.7, beta=6.0)
+    c = backend(D, ext, a=0.7, beta=6.0)
+    U = hot(o)
+    c.links_upload(U)
+    assert rel(c.staples(), o.staples(U)) <= RTOL
+    assert rel(c.force(), o.force(U, literal=True)) <= RTOL
+
+
+@pytest.mark.parametrize("D,ext", [(4, [4, 4, 4, 4]), (3, [6, 6, 6]), (4, [4, 6, 2, 8]), (4, [5, 5, 5, 5])])
+def test_md_steps(backend, D, ext):
+    o = Oracle(D, ext, a=1.0, beta=6.0)
+    c = backend(D, ext, a=1.0, beta=6.0)
+    U = hot(o)
+    E = o.momenta_refresh(SEED_RNG, 2, sigma=0.7)
+    c.links_upload(U)
+    c.efield_upload(E)
+    c.efield_step(0.01)
+    E1 = o.efield_step(U, E, 0.01)
+    assert rel(c.efield_download(), E1) <= RTOL
+    c.link_step(0.01)
+    U1 = o.link_step(U, E1, 0.01)
+    assert rel(c.links_download(), U1) <= RTOL
+    c.links_upload(U)
+    c.link_step(0.05, use_exp=True)
+    assert rel(c.links_download(), o.link_step_exp(U, E1, 0.05)) <= RTOL
+    for kind, name in enumerate(["sync_sync", "leap_leap", "sync_leap", "leap_sync", "symplectic"]):
+        c.links_upload(U)
+        c.efield_upload(E)
+        c.integrate(kind, 0.01)
+        Uo, Eo = o.integrate(U, E, name, 0.01)
+        assert rel(c.links_download(), Uo) <= RTOL, name
+        assert rel(c.efield_download(), Eo) <= RTOL, name
+
+
+def test_symplectic_trajectory_and_merge_equivalence(backend):
+    """n-step trajectory (state.rs:470-492): fused + merged-kick schedule is BIT-identical to the literal
+    3-kernel-per-step schedule, and both match the oracle to 1e-12."""
+    from lattice_qcd_rs_b200 import FLAG_NO_KICK_MERGE
+    D, ext = 4, [4, 4, 4, 4]
+    o = Oracle(D, ext, a=1.0, beta=6.0)
+    U = hot(o)
+    E = o.momenta_refresh(SEED_RNG, 3)
+    out = []
+    for flags in (0, FLAG_NO_KICK_MERGE):
+        c = backend(D, ext, a=1.0, beta=6.0)
+        c.set_flags(flags)
+        c.links_upload(U)
+        c.efield_upload(E)
+        c.symplectic_n(0.01, 10)
+        assert c.t == 10
+        out.append((c.links_download(), c.efield_download(), c.kernel_launches))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][2] < out[1][2]
+    Uo, Eo = o.integrate(U, E, "symplectic", 0.01, n=10)
+    assert rel(out[0][0], Uo) <= RTOL and rel(out[0][1], Eo) <= RTOL
+    c = backend(D, ext, a=1.0, beta=6.0)
+    c.links_upload(U)
+    c.efield_upload(E)
+    c.leapfrog_n(0.01, 5)
+    Uo, Eo = o.leapfrog_n(U, E, 0.01, 5)
+    assert rel(c.links_download(), Uo) <= RTOL and rel(c.efield_download(), Eo) <= RTOL
+
+
+def test_leap_frog_energy_conservation(backend):
+    """test_leap_frog (test/mod.rs:679-698): 4^4, a=1000, beta=1: |dH| < 1e-5 after one leapfrog step dt=0.01."""
+    o = Oracle(4, 4, a=1000.0, beta=1.0)
+    c = backend(4, 4, a=1000.0, beta=1.0)
+    U = hot(o, 0)
+    c.links_upload(U)
+    c.momenta_refresh(0, 0)
+    c.gauss_project()
+    h0 = c.hamiltonian_total()
+    c.leapfrog_n(0.01, 1)
+    assert abs(c.hamiltonian_total() - h0) < 1e-5
+
+
+def test_reunitarize(backend):
+    o = Oracle(4, 4)
+    c = backend(4, 4)
+    rng = np.random.default_rng(5)
+    U = rng.uniform(-2, 2, (o.nl, 18))
+    U[0] = 0.0  # the `norm <= eps: leave unchanged` branch of su3.rs:284-294
+    U[1] = 0.0
+    U[1][0] = 2.0
+    c.links_upload(U)
+    c.reunitarize()
+    got, want = c.links_download(), o.normalize_links(U)
+    assert rel(got, want) <= RTOL
+    assert np.array_equal(got[0], np.zeros(18))
+    assert np.array_equal(got[1], np.eye(18)[0])
+    # drift off SU(3) along a trajectory, then reproject: matches the oracle doing the same
+    U = hot(o)
+    E = o.momenta_refresh(1, 1, sigma=1.0)
+    c.links_upload(U)
+    c.efield_upload(E)
+    c.symplectic_n(0.05, 4)
+    c.reunitarize()
+    Uo, _ = o.integrate(U, E, "symplectic", 0.05, n=4)
+    assert rel(c.links_download(), o.normalize_links(Uo)) <= 1e-11
+
+
+@pytest.mark.parametrize("D,ext", [(4, [4, 4, 4, 4]), (3, [6, 4, 8])])
+def test_start_configs_and_momenta(backend, D, ext):
+    o = Oracle(D, ext, beta=6.0)
+    c = backend(D, ext, beta=6.0)
+    c.links_set_random(SEED_RNG, 7)
+    assert rel(c.links_download(), o.links_random(SEED_RNG, 7)) <= 1e-13
+    c.momenta_refresh(SEED_RNG, 9)
+    Eo = o.momenta_refresh(SEED_RNG, 9)
+    assert np.abs(c.efield_download() - Eo).max() <= 1e-14
+    assert abs(Eo.std() - 0.5 / 6.0) < 0.01  # sigma = 0.5/beta (state.rs:1097)
+
+
+@pytest.mark.parametrize("D,ext", [(4, [4, 4, 4, 4]), (3, [6, 6, 6]), (4, [4, 6, 2, 8])])
+def test_gauss(backend, D, ext):
+    o = Oracle(D, ext, a=1.0, beta=2.0)
+    c = backend(D, ext, a=1.0, beta=2.0)
+    U = hot(o)
+    E = o.momenta_refresh(SEED_RNG, 4)
+    c.links_upload(U)
+    c.efield_upload(E)
+    assert rel(c.gauss_field(), o.gauss_field(U, E)) <= RTOL
+    assert abs(c.gauss_sum_div() - o.gauss_sum_div(U, E)) <= RTOL * o.gauss_sum_div(U, E)
+    c.gauss_project_step()
+    E1 = o.project_to_gauss_step(U, E)
+    assert rel(c.efield_download(), E1) <= RTOL
+    c.efield_upload(E)
+    it = c.gauss_project()
+    Eo, ito = o.project_to_gauss(U, E)
+    assert it == ito
+    assert rel(c.efield_download(), Eo) <= 1e-10
+    assert c.gauss_sum_div() <= np.finfo(float).eps * o.ns * 320 * 1.0000001
+
+
+@pytest.mark.parametrize("D,ext", [(4, [4, 4, 4, 4]), (3, [6, 6, 6]), (2, [8, 8]), (4, [4, 6, 2, 8])])
+def test_sweeps_match_oracle_checkerboard(backend, D, ext):
+    o = Oracle(D, ext, a=1.0, beta=6.0)
+    c = backend(D, ext, a=1.0, beta=6.0)
+    U = hot(o)
+    # heat bath (heat_bath.rs:73-123), reference coupling beta*k
+    c.links_upload(U)
+    c.sweep_heatbath(SEED_RNG, 11)
+    Uo = o.sweep_heatbath(U, SEED_RNG, 11, order=1, per_link=True)
+    assert rel(c.links_download(), Uo) <= 1e-9
+    # Wilson-correct coupling scale
+    c.links_upload(U)
+    c.sweep_heatbath(SEED_RNG, 12, coupling_scale=1.0 / 3.0)
+    assert rel(c.links_download(), o.sweep_heatbath(U, SEED_RNG, 12, coupling_scale=1.0 / 3.0)) <= 1e-9
+    # over-relaxation (overrelaxation.rs:86-98, 158-171)
+    for kind in (0, 1):
+        c.links_upload(U)
+        c.sweep_overrelax(kind)
+        assert rel(c.links_download(), o.sweep_overrelax(U, kind, order=1)) <= 1e-9
+    # Metropolis (metropolis_hastings_sweep.rs:126-174) with its diagnostics
+    for n_update, spread in ((1, 0.1), (3, 0.25)):
+        c.links_upload(U)
+        na, sp = c.sweep_metropolis(SEED_RNG, 13, spread=spread, n_update=n_update)
+        Uo, nao, spo = o.sweep_metropolis(U, SEED_RNG, 13, n_update=n_update, spread=spread, order=1, per_link=True)
+        assert na == nao and abs(sp - spo) <= 1e-9 * max(spo, 1.0)
+        assert rel(c.links_download(), Uo) <= 1e-9
+
+
+def test_pauli3_flag(backend):
+    from lattice_qcd_rs_b200 import FLAG_PAULI3_FIXED
+    o = Oracle(4, 4, beta=6.0)
+    c = backend(4, 4, beta=6.0)
+    U = hot(o)
+    try:
+        o.set_flags(Oracle.FLAG_PAULI3_FIXED)
+        c.set_flags(FLAG_PAULI3_FIXED)
+        c.links_upload(U)
+        c.sweep_heatbath(SEED_RNG, 21)
+        assert rel(c.links_download(), o.sweep_heatbath(U, SEED_RNG, 21)) <= 1e-9
+    finally:
+        o.set_flags(0)
+
+
+def test_overrelax_conserves_action(backend):
+    """same_energy_reverse / same_energy_rotation (overrelaxation.rs:220-253)."""
+    o = Oracle(3, 4, beta=1.0)
+    c = backend(3, 4, beta=1.0)
+    c.links_upload(hot(o))
+    h = c.hamiltonian_links()
+    for kind in (0, 1):
+        c.sweep_overrelax(kind)
+        h2 = c.hamiltonian_links()
+        assert abs(h - h2) < np.finfo(float).eps * 100 * 4 ** 3 * (h + h2) * 0.5 * 10
+        h = h2
+
+
+def test_delta_s_equals_delta_h(backend):
+    """test_mh_delta (metropolis_hastings.rs:480-514): staple-based dS == H_links(new) - H_links(old)."""
+    o = Oracle(4, 4, beta=2.0)
+    c = backend(4, 4, beta=2.0)
+    U = hot(o)
+    c.links_upload(U)
+    A = c.staples()
+    h0 = c.hamiltonian_links()
+    from oracle.oracle import to_c
+    for l in (0, 17, 333, o.nl - 1):
+        new = o.links_random(99)[l]
+        ds = o.delta_s(to_c(A[l])[0], to_c(new)[0], to_c(U[l])[0])
+        V = U.copy()
+        V[l] = new
+        c.links_upload(V)
+        assert abs(ds - (c.hamiltonian_links() - h0)) < 1e-8
+
+
+def test_hmc_trajectory(backend):
+    """HybridMonteCarloDiagnostic::next_element (hybrid_monte_carlo.rs:465-471, 573-613) vs the oracle, from the
+    same start configuration and the same Philox momenta."""
+    o = Oracle(4, 4, a=1.0, beta=6.0)
+    c = backend(4, 4, a=1.0, beta=6.0)
+    U = hot(o)
+    c.links_upload(U)
+    for k in range(3):
+        r = c.hmc_trajectory(0.01, 10, SEED_RNG, k)
+        ro = o.hmc_trajectory(U, 0.01, 10, SEED_RNG, k)
+        assert r["gauss_steps"] == ro["gauss_steps"]
+        assert abs(r["h_old"] - ro["h_old"]) <= 1e-11 * abs(ro["h_old"])
+        assert abs(r["h_new"] - ro["h_new"]) <= 1e-11 * abs(ro["h_new"])
+        assert abs(r["prob"] - ro["prob"]) <= 1e-6
+        assert r["accepted"] == ro["accepted"]
+        U = ro["U"]
+        assert rel(c.links_download(), U) <= 1e-10
+    # reject path: absurd step size -> prob 0 -> links restored bit-exactly
+    before = c.links_download()
+    r = c.hmc_trajectory(1.0, 3, SEED_RNG, 99)
+    assert not r["accepted"] and r["prob"] < 1e-6 and np.isfinite(r["h_new"])
+    assert np.array_equal(c.links_download(), before)
+
+
+def test_snapshot_restore(backend):
+    o = Oracle(3, 4, beta=6.0)
+    c = backend(3, 4, beta=6.0)
+    U, E = hot(o), o.momenta_refresh(1, 2)
+    c.links_upload(U)
+    c.efield_upload(E)
+    c.set_t(5)
+    c.snapshot()
+    c.symplectic_n(0.02, 3)
+    assert c.t == 8 and not np.array_equal(c.links_download(), U)
+    c.restore()
+    assert c.t == 5 and np.array_equal(c.links_download(), U) and np.array_equal(c.efield_download(), E)
