@@ -163,6 +163,24 @@ int lq_halo_pack(lq_ctx*, int which, int dir, int side, void* d_buf, int64_t byt
 int lq_halo_unpack(lq_ctx*, int which, int dir, int side, const void* d_buf, int64_t bytes);
 int lq_halo_invalidate(lq_ctx*, int which);
 
+/* ---- measurement ---------------------------------------------------------------------------------------------
+ * Optional CUDA-event timing of kernel classes on the context stream (used by bench.py for the roofline line:
+ * one event pair around every launch of the class, summed on query).  Off by default. */
+enum {
+  LQ_PROF_EFIELD_LINK_STEP = 0, /* fused force + E kick + link step (the dominant kernel of an MD trajectory) */
+  LQ_PROF_EFIELD_STEP = 1,
+  LQ_PROF_LINK_STEP = 2,
+  LQ_PROF_PLAQUETTE = 3,
+  LQ_PROF_GAUSS_FIELD = 4,
+  LQ_PROF_GAUSS_STEP = 5,
+  LQ_PROF_HEATBATH = 6,
+  LQ_PROF_OVERRELAX = 7,
+  LQ_PROF_METROPOLIS = 8
+};
+int lq_profile_enable(lq_ctx*, int on);
+int lq_profile_reset(lq_ctx*);
+int lq_profile_get(lq_ctx*, int kernel_class, int64_t* launches, double* total_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,7 +104,12 @@ SYMBOLS = {
     "lq_halo_pack": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int64]),
     "lq_halo_unpack": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int64]),
     "lq_halo_invalidate": (C.c_int, [_vp, C.c_int]),
+    "lq_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "lq_profile_reset": (C.c_int, [_vp]),
+    "lq_profile_get": (C.c_int, [_vp, C.c_int, _i64p, _dp]),
 }
+PROF = {"efield_link_step": 0, "efield_step": 1, "link_step": 2, "plaquette": 3, "gauss_field": 4, "gauss_step": 5,
+        "heatbath": 6, "overrelax": 7, "metropolis": 8}
 
 
 def bind(path):
@@ -251,8 +256,9 @@ class Context:
         U = _f64(U)
         self._check(self.lib.lq_links_upload(self._h, _p(U), U.size // 18), "lq_links_upload")
 
-    def links_download(self):
-        U = np.empty((self.nl, 18))
+    def links_download(self, out=None):
+        U = np.empty((self.nl, 18)) if out is None else out
+        assert U.dtype == np.float64 and U.flags["C_CONTIGUOUS"] and U.size == self.nl * 18
         self._check(self.lib.lq_links_download(self._h, _p(U), self.nl), "lq_links_download")
         return U
 
@@ -260,8 +266,9 @@ class Context:
         E = _f64(E)
         self._check(self.lib.lq_efield_upload(self._h, _p(E), E.size // 8), "lq_efield_upload")
 
-    def efield_download(self):
-        E = np.empty((self.nl, 8))
+    def efield_download(self, out=None):
+        E = np.empty((self.nl, 8)) if out is None else out
+        assert E.dtype == np.float64 and E.flags["C_CONTIGUOUS"] and E.size == self.nl * 8
         self._check(self.lib.lq_efield_download(self._h, _p(E), self.nl), "lq_efield_download")
         return E
 
@@ -389,6 +396,18 @@ class Context:
                                                int(do_project), C.byref(h0), C.byref(h1), C.byref(p), C.byref(acc),
                                                C.byref(gs)), "lq_hmc_trajectory")
         return dict(h_old=h0.value, h_new=h1.value, prob=p.value, accepted=bool(acc.value), gauss_steps=gs.value)
+
+    # -- measurement
+    def profile_enable(self, on=True):
+        self._check(self.lib.lq_profile_enable(self._h, int(on)), "lq_profile_enable")
+
+    def profile_reset(self):
+        self._check(self.lib.lq_profile_reset(self._h), "lq_profile_reset")
+
+    def profile_get(self, kernel):
+        n, ms = C.c_int64(0), C.c_double(0)
+        self._check(self.lib.lq_profile_get(self._h, PROF[kernel], C.byref(n), C.byref(ms)), "lq_profile_get")
+        return n.value, ms.value
 
     # -- halos
     def is_decomposed(self, d):

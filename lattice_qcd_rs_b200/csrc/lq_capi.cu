@@ -19,6 +19,7 @@
 
 #define LQ_BLOCK 128
 #define LQ_RBLOCK 256
+#define LQ_PROF_CAP 8192
 
 static thread_local char g_cuda_err[512] = "";
 
@@ -111,6 +112,13 @@ struct lq_ctx {
   bool halo_ok[3];
   lq_comm comm;
   bool has_comm;
+  // optional per-kernel-class CUDA-event timing (lq_profile_*)
+  bool prof_on;
+  int prof_n;                 // event pairs recorded since the last reset
+#ifndef LQ_HOST_EMU
+  cudaEvent_t* prof_ev;       // 2 * LQ_PROF_CAP events
+#endif
+  int prof_class[LQ_PROF_CAP];
   size_t u_bytes() const { return (size_t)g.pitch * 9 * g.D * sizeof(cx); }
   size_t e_bytes() const { return (size_t)g.pitch * 4 * g.D * sizeof(cx); }
   size_t g_bytes() const { return (size_t)g.pitch * 9 * sizeof(cx); }
@@ -134,6 +142,28 @@ struct DeviceGuard {
   do {              \
   } while (0)
 #endif
+
+// Times the launches issued while it is alive (one CUDA-event pair on the context stream) when profiling is on.
+struct ProfScope {
+  lq_ctx* c;
+  int slot;
+  ProfScope(lq_ctx* c_, int cls) : c(c_), slot(-1) {
+#ifndef LQ_HOST_EMU
+    if (c->prof_on && c->prof_ev && c->prof_n < LQ_PROF_CAP) {
+      slot = c->prof_n++;
+      c->prof_class[slot] = cls;
+      cudaEventRecord(c->prof_ev[2 * slot], c->stream);
+    }
+#else
+    (void)cls;
+#endif
+  }
+  ~ProfScope() {
+#ifndef LQ_HOST_EMU
+    if (slot >= 0) cudaEventRecord(c->prof_ev[2 * slot + 1], c->stream);
+#endif
+  }
+};
 
 // ------------------------------------------------------------------------------------------------ launchers
 #ifdef LQ_HOST_EMU
@@ -431,6 +461,11 @@ int lq_ctx_destroy(lq_ctx* c) {
   rt_free(c->d_result);
   rt_free_host(c->h_result);
 #ifndef LQ_HOST_EMU
+  if (c->prof_ev) {
+    for (int i = 0; i < 2 * LQ_PROF_CAP; ++i)
+      if (c->prof_ev[i]) cudaEventDestroy(c->prof_ev[i]);
+    free(c->prof_ev);
+  }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 #endif
   delete c;
@@ -602,6 +637,7 @@ int lq_links_set_random(lq_ctx* c, uint64_t seed, uint64_t counter) {
 // ---------------------------------------------------------------------------------------------- observables
 static int plaquette_all(lq_ctx* c, double v[3]) {
   LQ_TRY(ensure_halo(c, 0));
+  ProfScope ps(c, LQ_PROF_PLAQUETTE);
   LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol, KPlaquette<DD>{c->g, c->U, c->CA}))));
   for (int k = 0; k < 3; ++k) v[k] = c->h_result[k];
   return global_sum(c, v, 3);
@@ -678,6 +714,7 @@ int lq_force(lq_ctx* c, double* aos_out, int64_t n_links) {
 }
 static int efield_step(lq_ctx* c, double dt, int nkick) {
   LQ_TRY(ensure_halo(c, 0));
+  ProfScope ps(c, LQ_PROF_EFIELD_STEP);
 #ifdef LQ_TUNED
   if (c->g.D == 4) {
     LQ_TRY(lq_tuned_efield_step(c->stream, c->g, c->U, c->E, force_coef(c), dt, nkick));
@@ -691,6 +728,7 @@ static int efield_step(lq_ctx* c, double dt, int nkick) {
   return LQ_OK;
 }
 static int link_step(lq_ctx* c, const cx* Uin, cx* Uout, double dt, int use_exp) {
+  ProfScope ps(c, LQ_PROF_LINK_STEP);
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinkStep<DD>{c->g, Uin, Uout, c->E, dt, link_coef(c), use_exp}))));
   c->halo_ok[0] = false;
   return LQ_OK;
@@ -699,6 +737,7 @@ static int link_step(lq_ctx* c, const cx* Uin, cx* Uout, double dt, int use_exp)
 static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u) {
   LQ_TRY(ensure_halo(c, 0));
   LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
+  ProfScope ps(c, LQ_PROF_EFIELD_LINK_STEP);
 #ifdef LQ_TUNED
   if (c->g.D == 4) {
     LQ_TRY(lq_tuned_efield_link_step(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u, link_coef(c), nkick));
@@ -808,6 +847,7 @@ static int gauss_field(lq_ctx* c) {
   LQ_TRY(ensure_buf(&c->G, c->g_bytes(), c));
   LQ_TRY(ensure_halo(c, 0));
   LQ_TRY(ensure_halo(c, 1));
+  ProfScope ps(c, LQ_PROF_GAUSS_FIELD);
   LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussField<DD>{c->g, c->U, c->E, c->G}))));
   c->halo_ok[2] = false;
   return LQ_OK;
@@ -839,6 +879,7 @@ int lq_gauss_project_step(lq_ctx* c) {
   LQ_TRY(gauss_field(c));
   LQ_TRY(ensure_halo(c, 2));
   LQ_TRY(ensure_buf(&c->E2, c->e_bytes(), c));
+  ProfScope ps(c, LQ_PROF_GAUSS_STEP);
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KGaussProjectStep<DD>{c->g, c->U, c->G, c->E, c->E2}))));
   cx* t = c->E;
   c->E = c->E2;
@@ -882,6 +923,7 @@ int lq_sweep_heatbath(lq_ctx* c, uint64_t seed, uint64_t counter, double couplin
   for (int d = 0; d < c->g.D; ++d)
     for (int p = 0; p < 2; ++p) {
       LQ_TRY(ensure_halo(c, 0));
+      ProfScope ps(c, LQ_PROF_HEATBATH);
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2,
                                      KHeatBath<DD>{c->g, c->U, d, p, c->flags, c->beta * coupling_scale, seed, counter}))));
       c->halo_ok[0] = false;
@@ -895,6 +937,7 @@ int lq_sweep_overrelax(lq_ctx* c, int kind) {
   for (int d = 0; d < c->g.D; ++d)
     for (int p = 0; p < 2; ++p) {
       LQ_TRY(ensure_halo(c, 0));
+      ProfScope ps(c, LQ_PROF_OVERRELAX);
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2, KOverrelax<DD>{c->g, c->U, d, p, kind}))));
       c->halo_ok[0] = false;
     }
@@ -909,6 +952,7 @@ int lq_sweep_metropolis(lq_ctx* c, uint64_t seed, uint64_t counter, double sprea
   for (int d = 0; d < c->g.D; ++d)
     for (int p = 0; p < 2; ++p) {
       LQ_TRY(ensure_halo(c, 0));
+      ProfScope ps(c, LQ_PROF_METROPOLIS);
       LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol / 2,
                                      KMetropolis<DD>{c->g, c->U, d, p, c->flags, n_update, c->beta, c->CA, spread, seed,
                                                      counter}))));
@@ -974,6 +1018,44 @@ int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint
   if (h_new) *h_new = h1;
   if (prob) *prob = p;
   if (accepted) *accepted = ok ? 1 : 0;
+  return LQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- profiling
+int lq_profile_enable(lq_ctx* c, int on) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+#ifndef LQ_HOST_EMU
+  if (on && !c->prof_ev) {
+    c->prof_ev = (cudaEvent_t*)calloc(2 * LQ_PROF_CAP, sizeof(cudaEvent_t));
+    if (!c->prof_ev) return LQ_E_CUDA;
+    for (int i = 0; i < 2 * LQ_PROF_CAP; ++i) LQ_CHECK(cudaEventCreate(&c->prof_ev[i]));
+  }
+#endif
+  c->prof_on = on != 0;
+  c->prof_n = 0;
+  return LQ_OK;
+}
+int lq_profile_reset(lq_ctx* c) {
+  if (!c) return LQ_E_BADARG;
+  c->prof_n = 0;
+  return LQ_OK;
+}
+int lq_profile_get(lq_ctx* c, int kernel_class, int64_t* launches, double* total_ms) {
+  if (!c || !launches || !total_ms) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  *launches = 0;
+  *total_ms = 0.0;
+#ifndef LQ_HOST_EMU
+  LQ_TRY(rt_sync(c->stream));
+  for (int i = 0; i < c->prof_n; ++i) {
+    if (c->prof_class[i] != kernel_class) continue;
+    float ms = 0.f;
+    LQ_CHECK(cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+    *total_ms += ms;
+    *launches += 1;
+  }
+#endif
   return LQ_OK;
 }
 
