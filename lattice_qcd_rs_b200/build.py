@@ -14,7 +14,10 @@ LIB = os.path.join(HERE, "liblqcd_b200.so")
 SRCS = ["lq_capi.cu"]
 DEPS = ["lq_capi.cu", "lq_kernels.cuh", "lq_common.cuh", "lq_local.cuh", "lq_tuned.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared", "--use_fast_math=false" if False else "-DLQ_BUILD_CUDA=1"]
+              "-shared", "-DLQ_BUILD_CUDA=1"]
+
+
+USE_TUNED = False  # flipped on once lq_tuned.cuh exports the launchers (lq_tuned_efield_step, ...)
 
 
 def nvcc():
@@ -36,7 +39,7 @@ def build(force=False, verbose=False):
     if not (force or needs_build()):
         return LIB
     flags = list(NVCC_FLAGS)
-    if os.path.exists(os.path.join(CSRC, "lq_tuned.cuh")):
+    if USE_TUNED:
         flags.append("-DLQ_HAVE_TUNED=1")
     if verbose:
         flags += ["-Xptxas", "-v"]

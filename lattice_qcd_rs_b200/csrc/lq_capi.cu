@@ -6,6 +6,7 @@
 // (tests/emu.py); the package never loads it.
 #include "../../include/lqcd_b200.h"
 #include "lq_kernels.cuh"
+#include "lq_geom_host.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -316,45 +317,6 @@ static int ensure_buf(cx** p, size_t bytes, lq_ctx* c) {
   if (*p) return LQ_OK;
   LQ_TRY(rt_malloc((void**)p, bytes));
   return rt_memset(*p, 0, bytes, c->stream);
-}
-
-static int init_geom(LqGeom& g, int D, const int64_t* gext, const int* nproc, const int* coord) {
-  if (D < 2 || D > LQ_MAXD) return LQ_E_BADARG;
-  memset(&g, 0, sizeof(g));
-  g.D = D;
-  lq_i64 ss = 1, gs = 1, ls = 1;
-  for (int d = 0; d < LQ_MAXD; ++d) {
-    if (d < D) {
-      if (gext[d] < 2 || gext[d] > (1 << 20)) return LQ_E_BADARG;  // LatticeCyclic::new needs dim >= 2 (lattice.rs:190-201)
-      int np = nproc ? nproc[d] : 1;
-      if (np < 1 || gext[d] % np != 0) return LQ_E_BADARG;
-      if (np > 1 && d < D - 2) return LQ_E_BADARG;  // only the two slowest directions may be split
-      if (np > 1 && d == 0) return LQ_E_BADARG;
-      g.gext[d] = (int)gext[d];
-      g.ext[d] = (int)(gext[d] / np);
-      if (np > 1 && g.ext[d] < 2) return LQ_E_BADARG;
-      g.ghost[d] = np > 1 ? 1 : 0;
-      g.goff[d] = np > 1 ? coord[d] * g.ext[d] : 0;
-      if (np > 1 && (coord[d] < 0 || coord[d] >= np)) return LQ_E_BADARG;
-    } else {
-      g.gext[d] = g.ext[d] = 1;
-      g.ghost[d] = 0;
-      g.goff[d] = 0;
-    }
-    g.sext[d] = g.ext[d] + 2 * g.ghost[d];
-    g.sstride[d] = ss;
-    g.gstride[d] = gs;
-    g.lstride[d] = ls;
-    ss *= g.sext[d];
-    gs *= g.gext[d];
-    ls *= g.ext[d];
-  }
-  g.vol = ls;
-  g.svol = ss;
-  g.half = ((g.svol + 1) / 2 + 7) & ~(lq_i64)7;  // keep the odd half 128-byte aligned
-  g.pitch = 2 * g.half;
-  g.ne0 = (g.ext[0] + 1) / 2;
-  return LQ_OK;
 }
 
 static int ctx_create_common(lq_ctx** out, int device, int D, const int64_t* gext, const int* nproc, const int* coord,

@@ -53,6 +53,7 @@ struct LqGeom {
   int gext[LQ_MAXD];   // global extents
   int goff[LQ_MAXD];   // global coordinate of the local interior origin
   lq_i64 sstride[LQ_MAXD];
+  lq_i64 nstride[LQ_MAXD];  // stride used by the neighbour shifts (== sstride; tools/kbench zeroes it for a locality bound)
   lq_i64 gstride[LQ_MAXD];
   lq_i64 lstride[LQ_MAXD];  // strides of the rank-local interior block in reference order (AoS boundary)
   lq_i64 vol;               // interior sites
@@ -60,6 +61,11 @@ struct LqGeom {
   lq_i64 half;              // start of the odd-s half inside a plane
   lq_i64 pitch;             // plane length (elements)
   int ne0;                  // even-x0 sites per row = (ext0+1)/2
+  // thread -> site mapping of the tuned kernels: the lattice is walked tile by tile (tile[d] divides ext[d],
+  // tile[0] even) so that the sites a thread block touches form a compact 4-D brick (L1 reuse of neighbours).
+  int tile[LQ_MAXD];
+  int ntile[LQ_MAXD];
+  int tvol;
 };
 
 template <int D>
@@ -86,6 +92,31 @@ LQ_HD Site<D> lq_site(const LqGeom& g, lq_i64 n) {
     int xd = (int)(row - q * g.ext[d]);
     row = q;
     st.x[d] = xd + g.ghost[d];
+    st.s += (lq_i64)st.x[d] * g.sstride[d];
+  }
+  return st;
+}
+// n in [0, vol) -> site, walking the lattice tile by tile; inside a tile x0 runs "even first, then odd".
+template <int D>
+LQ_HD Site<D> lq_site_tiled(const LqGeom& g, lq_i64 n) {
+  Site<D> st;
+  lq_i64 tid = n / g.tvol;
+  int w = (int)(n - tid * g.tvol);
+  int h0 = g.tile[0] >> 1;
+  int w0 = w % g.tile[0];
+  w /= g.tile[0];
+  int x0l = w0 < h0 ? 2 * w0 : 2 * (w0 - h0) + 1;
+  int t0 = (int)(tid % g.ntile[0]);
+  tid /= g.ntile[0];
+  st.x[0] = t0 * g.tile[0] + x0l + g.ghost[0];
+  st.s = st.x[0];
+#pragma unroll
+  for (int d = 1; d < D; ++d) {
+    int wd = w % g.tile[d];
+    w /= g.tile[d];
+    int td = (int)(tid % g.ntile[d]);
+    tid /= g.ntile[d];
+    st.x[d] = td * g.tile[d] + wd + g.ghost[d];
     st.s += (lq_i64)st.x[d] * g.sstride[d];
   }
   return st;
@@ -120,9 +151,9 @@ template <int D>
 LQ_HD Site<D> lq_up(const LqGeom& g, Site<D> st, int d) {
   if (st.x[d] + 1 < g.sext[d]) {
     st.x[d] += 1;
-    st.s += g.sstride[d];
+    st.s += g.nstride[d];
   } else {
-    st.s -= (lq_i64)st.x[d] * g.sstride[d];
+    st.s -= (lq_i64)st.x[d] * g.nstride[d];
     st.x[d] = 0;
   }
   return st;
@@ -131,10 +162,10 @@ template <int D>
 LQ_HD Site<D> lq_dn(const LqGeom& g, Site<D> st, int d) {
   if (st.x[d] > 0) {
     st.x[d] -= 1;
-    st.s -= g.sstride[d];
+    st.s -= g.nstride[d];
   } else {
     st.x[d] = g.sext[d] - 1;
-    st.s += (lq_i64)st.x[d] * g.sstride[d];
+    st.s += (lq_i64)st.x[d] * g.nstride[d];
   }
   return st;
 }

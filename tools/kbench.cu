@@ -1,0 +1,244 @@
+// tools/kbench.cu -- micro-benchmark of the MD hot-loop kernel variants on one GPU (development tool).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I lattice_qcd_rs_b200/csrc tools/kbench.cu -o tools/kbench
+//   tools/kbench [extent=32] [reps=10]
+// Every variant is checked against the generic functor kernel (KEfieldLinkStep) before it is timed.
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "lq_geom_host.h"
+#include "lq_tuned.cuh"
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+      exit(1);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+template <class F>
+__global__ void __launch_bounds__(128) gen_k(F f, lq_i64 n) {
+  lq_i64 i = (lq_i64)blockIdx.x * 128 + threadIdx.x;
+  if (i < n) f(i);
+}
+template <class F>
+static void gen_launch(lq_i64 n, const F& f) {
+  gen_k<F><<<(unsigned)((n + 127) / 128), 128>>>(f, n);
+  CK(cudaGetLastError());
+}
+
+// FP64 FMA peak: 8 independent chains per thread
+__global__ void dfma_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+// streaming copy (HBM peak on this box, double2)
+__global__ void copy_k(const double2* __restrict__ a, double2* __restrict__ b, lq_i64 n) {
+  lq_i64 i = (lq_i64)blockIdx.x * blockDim.x + threadIdx.x;
+  lq_i64 stride = (lq_i64)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) b[i] = a[i];
+}
+
+// L2 -> SM read bandwidth: every block streams the same 48 MiB window (L2 resident) with L1 bypass (ld.global.cg)
+__global__ void l2_read_k(const double2* __restrict__ a, lq_i64 n, int passes, double* out) {
+  double acc = 0.0;
+  for (int ps = 0; ps < passes; ++ps) {
+    lq_i64 i = ((lq_i64)blockIdx.x * 7919 * blockDim.x + threadIdx.x) % n;
+    for (lq_i64 k = 0; k < n / ((lq_i64)gridDim.x * blockDim.x) * 8; ++k) {
+      double2 v = __ldcg(a + i);
+      acc += v.x + v.y;
+      i += (lq_i64)blockDim.x * gridDim.x;
+      if (i >= n) i -= n;
+    }
+  }
+  if (acc == 1.2345e-300) out[0] = acc;
+}
+
+struct Variant {
+  std::string name;
+  std::function<void()> run;
+  const void* func;
+  int block;
+};
+
+int main(int argc, char** argv) {
+  int L = argc > 1 ? atoi(argv[1]) : 32;
+  int reps = argc > 2 ? atoi(argv[2]) : 10;
+  int64_t ext[4] = {L, L, L, L};
+  LqGeom g;
+  if (init_geom(g, 4, ext, nullptr, nullptr)) return 1;
+  int rowtile[4] = {L, 1, 1, 1};
+  lq_set_tile(g, rowtile);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device %s, %d SMs, L=%d, vol=%lld, links=%lld\n", prop.name, prop.multiProcessorCount, L, g.vol, g.vol * 4);
+
+  size_t ub = (size_t)g.pitch * 36 * sizeof(cx), eb = (size_t)g.pitch * 16 * sizeof(cx);
+  cx *U, *U2, *E, *E0, *Uref, *Eref;
+  CK(cudaMalloc(&U, ub)); CK(cudaMalloc(&U2, ub)); CK(cudaMalloc(&Uref, ub));
+  CK(cudaMalloc(&E, eb)); CK(cudaMalloc(&E0, eb)); CK(cudaMalloc(&Eref, eb));
+  CK(cudaMemset(U, 0, ub)); CK(cudaMemset(U2, 0, ub)); CK(cudaMemset(E, 0, eb));
+  gen_launch(lq_link_items(g), KLinksRandom<4>{g, U, 0x1234567ull, 0});
+  gen_launch(lq_link_items(g), KMomentaRefresh<4>{g, E0, 0x1234567ull, 1, 0.1});
+  CK(cudaDeviceSynchronize());
+  const double coef = -sqrt(2.0 / 3.0), c_u = sqrt(6.0), dt = 0.01;
+  const lq_i64 nl = g.vol * 4;
+
+  // ---- peaks on this box
+  {
+    double* out;
+    CK(cudaMalloc(&out, sizeof(double) * 148 * 8 * 256));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    int iters = 200000;
+    dfma_peak<<<148 * 8, 256>>>(out, 1000);
+    CK(cudaEventRecord(e0));
+    dfma_peak<<<148 * 8, 256>>>(out, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 8 * iters * 148.0 * 8 * 256;
+    printf("FP64 FMA peak: %.2f TFLOP/s (%.3f ms)\n", fl / ms / 1e9, ms);
+    lq_i64 n = (lq_i64)g.pitch * 36;
+    copy_k<<<148 * 16, 256>>>(U, U2, n);
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < 5; ++r) copy_k<<<148 * 16, 256>>>(U, U2, n);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("copy (read+write) : %.1f GB/s\n", 5.0 * 2 * n * 16 / ms / 1e6);
+    {
+      lq_i64 n2 = (lq_i64)48 * 1024 * 1024 / 16;
+      int blocks = 148 * 8, threads = 256, passes = 4;
+      l2_read_k<<<blocks, threads>>>(U, n2, 1, out);
+      CK(cudaEventRecord(e0));
+      l2_read_k<<<blocks, threads>>>(U, n2, passes, out);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      double bytes = (double)passes * (n2 / ((lq_i64)blocks * threads) * 8) * blocks * threads * 16.0;
+      printf("L2->SM read (48 MiB window, ld.cg): %.1f GB/s\n", bytes / ms / 1e6);
+    }
+    CK(cudaFree(out));
+  }
+
+  // ---- reference output from the generic functor kernel
+  CK(cudaMemcpy(E, E0, eb, cudaMemcpyDeviceToDevice));
+  gen_launch(lq_link_items(g), KEfieldLinkStep<4>{g, U, Uref, E, coef, dt / 2, dt, c_u, 2, 0});
+  CK(cudaMemcpy(Eref, E, eb, cudaMemcpyDeviceToDevice));
+  CK(cudaDeviceSynchronize());
+  std::vector<double> hUref(ub / 8), hEref(eb / 8), hU(ub / 8), hE(eb / 8);
+  CK(cudaMemcpy(hUref.data(), Uref, ub, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hEref.data(), Eref, eb, cudaMemcpyDeviceToHost));
+
+  std::vector<Variant> vs;
+  auto tiled = [&](int a, int b, int c, int d) {
+    LqGeom t = g;
+    int w[4] = {a, b, c, d};
+    lq_set_tile(t, w);
+    return t;
+  };
+  vs.push_back({"generic KEfieldLinkStep (block 128)", [&] { gen_launch(lq_link_items(g), KEfieldLinkStep<4>{g, U, U2, E, coef, dt / 2, dt, c_u, 2, 0}); },
+                (const void*)gen_k<KEfieldLinkStep<4>>, 128});
+#define V1(BLOCK, MINB, MAP, GEOM, LABEL)                                                                          \
+  vs.push_back({std::string("v1 block=" #BLOCK " minb=" #MINB " ") + LABEL,                                         \
+                [&, gg = GEOM] {                                                                                    \
+                  lq_md_link_kernel<BLOCK, MINB, MAP, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>( \
+                      gg, U, U2, E, coef, dt / 2, dt, c_u, 2);                                                      \
+                  CK(cudaGetLastError());                                                                           \
+                },                                                                                                  \
+                (const void*)lq_md_link_kernel<BLOCK, MINB, MAP, 1>, BLOCK})
+  V1(128, 1, 0, g, "row");
+  V1(128, 2, 0, g, "row");
+  V1(128, 3, 0, g, "row");
+  V1(128, 4, 0, g, "row");
+  V1(256, 1, 0, g, "row");
+  V1(256, 2, 0, g, "row");
+  V1(64, 4, 0, g, "row");
+  V1(64, 8, 0, g, "row");
+  V1(128, 3, 1, tiled(16, 2, 1, 1), "tile16x2x1x1");
+  V1(128, 3, 1, tiled(8, 2, 2, 1), "tile8x2x2x1");
+  V1(128, 3, 1, tiled(8, 4, 1, 1), "tile8x4x1x1");
+  V1(256, 2, 1, tiled(16, 2, 2, 1), "tile16x2x2x1");
+  V1(256, 2, 1, tiled(8, 2, 2, 2), "tile8x2x2x2");
+  V1(256, 2, 1, tiled(16, 4, 1, 1), "tile16x4x1x1");
+  V1(256, 2, 1, tiled(32, 2, 1, 1), "tile32x2x1x1");
+  V1(512, 1, 1, tiled(8, 4, 2, 2), "tile8x4x2x2");
+  V1(512, 1, 1, tiled(16, 2, 2, 2), "tile16x2x2x2");
+  V1(512, 1, 1, tiled(32, 2, 2, 1), "tile32x2x2x1");
+  {
+    LqGeom fake = g;  // neighbours in x1..x3 collapse onto the site itself: perfect-locality bound of this code
+    fake.nstride[1] = fake.nstride[2] = fake.nstride[3] = 0;
+    V1(128, 3, 0, fake, "row FAKE-LOCALITY (not a valid result)");
+    V1(256, 2, 0, fake, "row FAKE-LOCALITY (not a valid result)");
+  }
+#define V3(BLOCK, MINB, MAP, GEOM, LABEL)                                                                          \
+  vs.push_back({std::string("v3 nu-loop block=" #BLOCK " minb=" #MINB " ") + LABEL,                                 \
+                [&, gg = GEOM] {                                                                                    \
+                  lq_md_link_loop_kernel<BLOCK, MINB, MAP, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>( \
+                      gg, U, U2, E, coef, dt / 2, dt, c_u, 2);                                                      \
+                  CK(cudaGetLastError());                                                                           \
+                },                                                                                                  \
+                (const void*)lq_md_link_loop_kernel<BLOCK, MINB, MAP, 1>, BLOCK})
+  V3(128, 1, 0, g, "row");
+  V3(128, 3, 0, g, "row");
+  V3(128, 4, 0, g, "row");
+  V3(256, 1, 0, g, "row");
+  V3(256, 2, 0, g, "row");
+  V3(512, 1, 1, tiled(32, 2, 2, 1), "tile32x2x2x1");
+#define V2(MINB, MAP, GEOM, LABEL)                                                                           \
+  vs.push_back({std::string("v2 nu-split block=384 minb=" #MINB " ") + LABEL,                                 \
+                [&, gg = GEOM] {                                                                              \
+                  lq_md_nusplit_kernel<MINB, MAP, 1><<<(unsigned)((g.vol + 31) / 32), 384>>>(gg, U, U2, E, coef, \
+                                                                                             dt / 2, dt, c_u, 2); \
+                  CK(cudaGetLastError());                                                                     \
+                },                                                                                            \
+                (const void*)lq_md_nusplit_kernel<MINB, MAP, 1>, 384})
+  V2(1, 0, g, "row");
+  V2(2, 0, g, "row");
+  V2(1, 1, tiled(16, 2, 1, 1), "tile16x2x1x1");
+  V2(1, 1, tiled(8, 2, 2, 1), "tile8x2x2x1");
+
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  printf("%-52s %5s %4s %9s %9s %8s %10s %10s\n", "variant", "regs", "occ", "ms", "GB/s(alg)", "TF/s", "errE", "errU");
+  for (auto& v : vs) {
+    cudaFuncAttributes at;
+    CK(cudaFuncGetAttributes(&at, v.func));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.func, v.block, 0));
+    CK(cudaMemcpy(E, E0, eb, cudaMemcpyDeviceToDevice));
+    CK(cudaMemset(U2, 0, ub));
+    v.run();
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(hU.data(), U2, ub, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hE.data(), E, eb, cudaMemcpyDeviceToHost));
+    double errE = 0, errU = 0;
+    for (size_t i = 0; i < hE.size(); ++i) errE = fmax(errE, fabs(hE[i] - hEref[i]));
+    for (size_t i = 0; i < hU.size(); ++i) errU = fmax(errU, fabs(hU[i] - hUref[i]));
+    CK(cudaMemcpy(E, E0, eb, cudaMemcpyDeviceToDevice));
+    v.run();
+    v.run();
+    CK(cudaEventRecord(e0));
+    for (int r = 0; r < reps; ++r) v.run();
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= reps;
+    printf("%-52s %5d %4d %9.4f %9.1f %8.2f %10.2e %10.2e\n", v.name.c_str(), at.numRegs, occ * v.block / 32, ms,
+           416.0 * nl / ms / 1e6, 3148.0 * nl / ms / 1e9, errE, errU);
+    fflush(stdout);
+  }
+  return 0;
+}
