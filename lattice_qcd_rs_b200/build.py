@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-shared", "-DLQ_BUILD_CUDA=1"]
 
 
-USE_TUNED = False  # flipped on once lq_tuned.cuh exports the launchers (lq_tuned_efield_step, ...)
+USE_TUNED = True  # flipped on once lq_tuned.cuh exports the launchers (lq_tuned_efield_step, ...)
 
 
 def nvcc():

@@ -120,9 +120,9 @@ struct lq_ctx {
   cudaEvent_t* prof_ev;       // 2 * LQ_PROF_CAP events
 #endif
   int prof_class[LQ_PROF_CAP];
-  size_t u_bytes() const { return (size_t)g.pitch * 9 * g.D * sizeof(cx); }
-  size_t e_bytes() const { return (size_t)g.pitch * 4 * g.D * sizeof(cx); }
-  size_t g_bytes() const { return (size_t)g.pitch * 9 * sizeof(cx); }
+  size_t u_bytes() const { return (size_t)g.nchunk * 32 * 9 * g.D * sizeof(cx); }
+  size_t e_bytes() const { return (size_t)g.nchunk * 32 * 4 * g.D * sizeof(cx); }
+  size_t g_bytes() const { return (size_t)g.nchunk * 32 * 9 * sizeof(cx); }
 };
 
 #ifndef LQ_HOST_EMU
@@ -678,8 +678,8 @@ static int efield_step(lq_ctx* c, double dt, int nkick) {
   LQ_TRY(ensure_halo(c, 0));
   ProfScope ps(c, LQ_PROF_EFIELD_STEP);
 #ifdef LQ_TUNED
-  if (c->g.D == 4) {
-    LQ_TRY(lq_tuned_efield_step(c->stream, c->g, c->U, c->E, force_coef(c), dt, nkick));
+  if (lq_tuned_ok(c->g)) {
+    LQ_CHECK(lq_tuned_efield_step(c->stream, c->g, c->U, c->E, force_coef(c), dt, nkick));
     c->launches++;
     c->halo_ok[1] = false;
     return LQ_OK;
@@ -701,8 +701,9 @@ static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u) {
   LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
   ProfScope ps(c, LQ_PROF_EFIELD_LINK_STEP);
 #ifdef LQ_TUNED
-  if (c->g.D == 4) {
-    LQ_TRY(lq_tuned_efield_link_step(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u, link_coef(c), nkick));
+  if (lq_tuned_ok(c->g)) {
+    LQ_CHECK(lq_tuned_efield_link_step(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u, link_coef(c),
+                                       nkick));
     c->launches++;
   } else
 #endif

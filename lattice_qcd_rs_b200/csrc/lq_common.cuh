@@ -1,13 +1,18 @@
 // lq_common.cuh -- geometry, HBM layout and 3x3 complex f64 algebra shared by every kernel.
 //
-// HBM layout ("x0-parity-split SoA", f64 complex = double2, every access a 128-bit load/store):
-//   links : U[(dir*9 + k) * pitch + p]   k = 3*row + col          (9 planes of double2 per direction)
-//   efield: E[(dir*4 + q) * pitch + p]   (e_{2q}, e_{2q+1})       (4 planes of double2 per direction)
-//   gauss : G[k * pitch + p]
-//   p = phys(s) = (s & 1) * half + (s >> 1),  s = storage-lexicographic site index (x0 fastest, the
-//   reference's own order lattice.rs:909-916, over the extents + ghost layers of decomposed directions).
-//   With an even x0 extent s&1 == x0&1, so the sites of one checkerboard colour inside a row are contiguous
-//   in memory: whole-lattice kernels and even/odd sweeps both read/write fully used 32-byte sectors.
+// HBM layout ("chunked SoA", f64 complex = double2, every access a 128-bit load/store):
+//   a field with NPL planes per site is stored as  F[((p >> 5) * NPL + plane) * 32 + (p & 31)]
+//   i.e. chunks of 32 consecutive site slots, and inside a chunk plane-major: a warp reading one plane of 32
+//   consecutive slots reads 512 contiguous bytes, and the planes of one site sit at the compile-time stride of
+//   512 bytes (immediate offsets in the load instructions; one address computation per 3x3 matrix).
+//     links : NPL = 9*D, plane = dir*9 + k,  k = 3*row + col
+//     efield: NPL = 4*D, plane = dir*4 + q,  element q = (e_{2q}, e_{2q+1})
+//     gauss : NPL = 9
+//   slot p of a site: rows of x0 keep the reference's order (x0 fastest, lattice.rs:909-916, over the extents +
+//   ghost layers of decomposed directions) but inside a row the even-x0 sites come first, then the odd ones:
+//     p = (s - x0) + (x0 & 1) * ceil(ext0/2) + (x0 >> 1),   s = storage-lexicographic site index.
+//   The sites of one checkerboard colour inside a row are therefore contiguous: whole-lattice kernels and
+//   even/odd sweeps both read/write fully used sectors.
 //
 // Build modes:  default = CUDA (sm_100a).  -DLQ_HOST_EMU = the same kernel bodies run in plain host loops;
 // that build is TEST INFRASTRUCTURE (CPU CI of host logic / world_size-2 gloo tests) and is never loaded by
@@ -58,8 +63,7 @@ struct LqGeom {
   lq_i64 lstride[LQ_MAXD];  // strides of the rank-local interior block in reference order (AoS boundary)
   lq_i64 vol;               // interior sites
   lq_i64 svol;              // storage sites
-  lq_i64 half;              // start of the odd-s half inside a plane
-  lq_i64 pitch;             // plane length (elements)
+  lq_i64 nchunk;            // 32-slot chunks per field = ceil(svol / 32)
   int ne0;                  // even-x0 sites per row = (ext0+1)/2
   // thread -> site mapping of the tuned kernels: the lattice is walked tile by tile (tile[d] divides ext[d],
   // tile[0] even) so that the sites a thread block touches form a compact 4-D brick (L1 reuse of neighbours).
@@ -74,7 +78,17 @@ struct Site {
   int x[D];  // storage coordinates (interior coordinate + ghost)
 };
 
-LQ_HD lq_i64 lq_phys(const LqGeom& g, lq_i64 s) { return (s & 1) * g.half + (s >> 1); }
+// slot of a site (row-local parity split) and element address of (slot, plane) in a field of npl planes
+template <int D>
+LQ_HD lq_i64 lq_slot(const LqGeom& g, const Site<D>& st) {
+  const int x0 = st.x[0];
+  return (st.s - x0) + (x0 & 1) * g.ne0 + (x0 >> 1);
+}
+LQ_HD lq_i64 lq_slot_s(const LqGeom& g, lq_i64 s) {  // from the storage index alone (direction 0 is never ghosted)
+  const int x0 = (int)(s % g.sext[0]);
+  return (s - x0) + (x0 & 1) * g.ne0 + (x0 >> 1);
+}
+LQ_HD lq_i64 lq_addr(lq_i64 p, int npl, int plane) { return ((p >> 5) * npl + plane) * 32 + (p & 31); }
 
 // n in [0, vol) -> site.  Rows of x0 are walked "even x0 first, then odd x0" so that consecutive n (lanes of
 // a warp) touch consecutive memory in both halves of the plane.
@@ -326,42 +340,54 @@ LQ_HD cx m3_det(const M3& a) {
 // ---------------------------------------------------------------------------------------------- SoA access
 LQ_HD M3 lq_load_link(const cx* LQ_RESTRICT U, const LqGeom& g, int dir, lq_i64 p) {
   M3 r;
-  const cx* b = U + (lq_i64)dir * 9 * g.pitch + p;
+  const cx* b = U + lq_addr(p, 9 * g.D, dir * 9);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) r.e[k] = LQ_LDG(b + k * g.pitch);
+  for (int k = 0; k < 9; ++k) r.e[k] = LQ_LDG(b + k * 32);
   return r;
 }
 // plain (coherent) load: for kernels that also write the array they read
 LQ_HD M3 lq_load_link_rw(const cx* U, const LqGeom& g, int dir, lq_i64 p) {
   M3 r;
-  const cx* b = U + (lq_i64)dir * 9 * g.pitch + p;
+  const cx* b = U + lq_addr(p, 9 * g.D, dir * 9);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) r.e[k] = b[k * g.pitch];
+  for (int k = 0; k < 9; ++k) r.e[k] = b[k * 32];
   return r;
 }
 LQ_HD void lq_store_link(cx* U, const LqGeom& g, int dir, lq_i64 p, const M3& m) {
-  cx* b = U + (lq_i64)dir * 9 * g.pitch + p;
+  cx* b = U + lq_addr(p, 9 * g.D, dir * 9);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) b[k * g.pitch] = m.e[k];
+  for (int k = 0; k < 9; ++k) b[k * 32] = m.e[k];
+}
+LQ_HD M3 lq_load_g(const cx* G, lq_i64 p) {
+  M3 r;
+  const cx* b = G + lq_addr(p, 9, 0);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.e[k] = b[k * 32];
+  return r;
+}
+LQ_HD void lq_store_g(cx* G, lq_i64 p, const M3& m) {
+  cx* b = G + lq_addr(p, 9, 0);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) b[k * 32] = m.e[k];
 }
 struct A8 {
   double e[8];
 };
 LQ_HD A8 lq_load_e(const cx* E, const LqGeom& g, int dir, lq_i64 p) {
   A8 r;
-  const cx* b = E + (lq_i64)dir * 4 * g.pitch + p;
+  const cx* b = E + lq_addr(p, 4 * g.D, dir * 4);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    cx v = b[q * g.pitch];
+    cx v = b[q * 32];
     r.e[2 * q] = v.x;
     r.e[2 * q + 1] = v.y;
   }
   return r;
 }
 LQ_HD void lq_store_e(cx* E, const LqGeom& g, int dir, lq_i64 p, const A8& a) {
-  cx* b = E + (lq_i64)dir * 4 * g.pitch + p;
+  cx* b = E + lq_addr(p, 4 * g.D, dir * 4);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) b[q * g.pitch] = cmk(a.e[2 * q], a.e[2 * q + 1]);
+  for (int q = 0; q < 4; ++q) b[q * 32] = cmk(a.e[2 * q], a.e[2 * q + 1]);
 }
 
 // ---------------------------------------------------------------------------------------------- su(3) algebra

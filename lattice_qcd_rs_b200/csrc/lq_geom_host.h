@@ -39,8 +39,7 @@ static inline int init_geom(LqGeom& g, int D, const int64_t* gext, const int* np
   }
   g.vol = ls;
   g.svol = ss;
-  g.half = ((g.svol + 1) / 2 + 7) & ~(lq_i64)7;  // keep the odd half 128-byte aligned
-  g.pitch = 2 * g.half;
+  g.nchunk = (g.svol + 31) / 32;
   g.ne0 = (g.ext[0] + 1) / 2;
   return 0;
 }

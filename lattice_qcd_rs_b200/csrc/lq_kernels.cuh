@@ -53,19 +53,19 @@ LQ_HD M3 lq_staple_sum(const cx* LQ_RESTRICT U, const LqGeom& g, const Site<D>& 
     if (nu == mu) continue;
     {  // up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)
       Site<D> xpn = lq_up<D>(g, x, nu);
-      M3 a = lq_load_link(U, g, nu, lq_phys(g, xpm.s));
-      M3 b = lq_load_link(U, g, mu, lq_phys(g, xpn.s));
+      M3 a = lq_load_link(U, g, nu, lq_slot<D>(g, xpm));
+      M3 b = lq_load_link(U, g, mu, lq_slot<D>(g, xpn));
       M3 t = m3_mul_nd(a, b);
-      M3 c = lq_load_link(U, g, nu, lq_phys(g, x.s));
+      M3 c = lq_load_link(U, g, nu, lq_slot<D>(g, x));
       m3_fma_nd(acc, t, c);
     }
     {  // down:  U_nu^+(x+mu-nu) U_mu^+(x-nu) U_nu(x-nu) = (U_mu(x-nu) U_nu(x+mu-nu))^+ U_nu(x-nu)
       Site<D> xmn = lq_dn<D>(g, x, nu);
       Site<D> xpmmn = lq_dn<D>(g, xpm, nu);
-      M3 a = lq_load_link(U, g, mu, lq_phys(g, xmn.s));
-      M3 b = lq_load_link(U, g, nu, lq_phys(g, xpmmn.s));
+      M3 a = lq_load_link(U, g, mu, lq_slot<D>(g, xmn));
+      M3 b = lq_load_link(U, g, nu, lq_slot<D>(g, xpmmn));
       M3 t = m3_mul_nn(a, b);
-      M3 c = lq_load_link(U, g, nu, lq_phys(g, xmn.s));
+      M3 c = lq_load_link(U, g, nu, lq_slot<D>(g, xmn));
       m3_fma_dn(acc, t, c);
     }
   }
@@ -75,7 +75,7 @@ LQ_HD M3 lq_staple_sum(const cx* LQ_RESTRICT U, const LqGeom& g, const Site<D>& 
 template <int D>
 LQ_HD A8 lq_force_link(const cx* LQ_RESTRICT U, const LqGeom& g, const Site<D>& x, int mu, double coef) {
   M3 a = lq_staple_sum<D>(U, g, x, mu);
-  M3 u = lq_load_link(U, g, mu, lq_phys(g, x.s));
+  M3 u = lq_load_link(U, g, mu, lq_slot<D>(g, x));
   M3 w = m3_mul_nn(u, a);
   cx tr[8];
   lq_trace_gen(w, tr);
@@ -97,7 +97,7 @@ struct KLinksFromAos {  // LatticeStateNew::new / set_link_matrix upload (state.
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> st = lq_site<D>(g, n);
     lq_i64 l = lq_local_index<D>(g, st);
-    lq_store_link(U, g, dir, lq_phys(g, st.s), lq_m3_from_aos(aos + (l * D + dir) * 18));
+    lq_store_link(U, g, dir, lq_slot<D>(g, st), lq_m3_from_aos(aos + (l * D + dir) * 18));
   }
 };
 template <int D>
@@ -111,7 +111,7 @@ struct KLinksToAos {
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> st = lq_site<D>(g, n);
     lq_i64 l = lq_local_index<D>(g, st);
-    lq_m3_to_aos(aos + (l * D + dir) * 18, lq_load_link_rw(U, g, dir, lq_phys(g, st.s)));
+    lq_m3_to_aos(aos + (l * D + dir) * 18, lq_load_link_rw(U, g, dir, lq_slot<D>(g, st)));
   }
 };
 template <int D>
@@ -128,7 +128,7 @@ struct KEFromAos {
     A8 a;
 #pragma unroll
     for (int k = 0; k < 8; ++k) a.e[k] = aos[(l * D + dir) * 8 + k];
-    lq_store_e(E, g, dir, lq_phys(g, st.s), a);
+    lq_store_e(E, g, dir, lq_slot<D>(g, st), a);
   }
 };
 template <int D>
@@ -142,7 +142,7 @@ struct KEToAos {
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> st = lq_site<D>(g, n);
     lq_i64 l = lq_local_index<D>(g, st);
-    A8 a = lq_load_e(E, g, dir, lq_phys(g, st.s));
+    A8 a = lq_load_e(E, g, dir, lq_slot<D>(g, st));
 #pragma unroll
     for (int k = 0; k < 8; ++k) aos[(l * D + dir) * 8 + k] = a.e[k];
   }
@@ -156,7 +156,7 @@ struct KLinksCold {  // LatticeStateDefault::new_cold, state.rs:671-679
     int dir;
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> st = lq_site<D>(g, n);
-    lq_store_link(U, g, dir, lq_phys(g, st.s), m3_ident());
+    lq_store_link(U, g, dir, lq_slot<D>(g, st), m3_ident());
   }
 };
 template <int D>
@@ -170,7 +170,7 @@ struct KLinksRandom {  // LinkMatrix::new_determinist, field.rs:646-659
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> st = lq_site<D>(g, n);
     LqStream rng(seed, counter, (uint64_t)(lq_global_index<D>(g, st) * D + dir));
-    lq_store_link(U, g, dir, lq_phys(g, st.s), lq_random_su3(rng));
+    lq_store_link(U, g, dir, lq_slot<D>(g, st), lq_random_su3(rng));
   }
 };
 template <int D>
@@ -193,7 +193,7 @@ struct KMomentaRefresh {  // EField::new_determinist with Normal(0, sigma), fiel
       a.e[2 * k] = sigma * z0;
       a.e[2 * k + 1] = sigma * z1;
     }
-    lq_store_e(E, g, dir, lq_phys(g, st.s), a);
+    lq_store_e(E, g, dir, lq_slot<D>(g, st), a);
   }
 };
 
@@ -216,8 +216,8 @@ struct KPlaquette {
 #pragma unroll
       for (int j = i + 1; j < D; ++j) {
         Site<D> xpj = lq_up<D>(g, x, j);
-        M3 a = m3_mul_nn(lq_load_link(U, g, i, lq_phys(g, x.s)), lq_load_link(U, g, j, lq_phys(g, xpi.s)));
-        M3 b = m3_mul_nn(lq_load_link(U, g, j, lq_phys(g, x.s)), lq_load_link(U, g, i, lq_phys(g, xpj.s)));
+        M3 a = m3_mul_nn(lq_load_link(U, g, i, lq_slot<D>(g, x)), lq_load_link(U, g, j, lq_slot<D>(g, xpi)));
+        M3 b = m3_mul_nn(lq_load_link(U, g, j, lq_slot<D>(g, x)), lq_load_link(U, g, i, lq_slot<D>(g, xpj)));
         cx t = m3_trace_nd(a, b);
         sre += t.x;
         sim += t.y;
@@ -237,7 +237,7 @@ struct KEfieldEnergy {
   const cx* E;
   LQ_HD void operator()(lq_i64 n, double* v) const {
     Site<D> x = lq_site<D>(g, n);
-    lq_i64 p = lq_phys(g, x.s);
+    lq_i64 p = lq_slot<D>(g, x);
     double s = 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
@@ -299,7 +299,7 @@ struct KEfieldStep {
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> st = lq_site<D>(g, n);
     A8 f = lq_force_link<D>(U, g, st, dir, coef);
-    lq_i64 p = lq_phys(g, st.s);
+    lq_i64 p = lq_slot<D>(g, st);
     A8 e = lq_load_e(E, g, dir, p);
     for (int kk = 0; kk < nkick; ++kk) {
 #pragma unroll
@@ -340,7 +340,7 @@ struct KLinkStep {
     int dir;
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> st = lq_site<D>(g, n);
-    lq_i64 p = lq_phys(g, st.s);
+    lq_i64 p = lq_slot<D>(g, st);
     M3 u = lq_load_link_rw(Uin, g, dir, p);
     A8 e = lq_load_e(E, g, dir, p);
     lq_store_link(Uout, g, dir, p, lq_link_update<D>(u, e, dt, c_u, use_exp));
@@ -362,7 +362,7 @@ struct KEfieldLinkStep {
     int dir;
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> st = lq_site<D>(g, n);
-    lq_i64 p = lq_phys(g, st.s);
+    lq_i64 p = lq_slot<D>(g, st);
     M3 a = lq_staple_sum<D>(U, g, st, dir);
     M3 u = lq_load_link(U, g, dir, p);
     M3 w = m3_mul_nn(u, a);
@@ -386,7 +386,7 @@ struct KReunitarize {  // LinkMatrix::normalize, field.rs:897-901 -> orthonormal
     int dir;
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> st = lq_site<D>(g, n);
-    lq_i64 p = lq_phys(g, st.s);
+    lq_i64 p = lq_slot<D>(g, st);
     lq_store_link(U, g, dir, p, lq_orthonormalize(lq_load_link_rw(U, g, dir, p)));
   }
 };
@@ -396,12 +396,12 @@ struct KReunitarize {  // LinkMatrix::normalize, field.rs:897-901 -> orthonormal
 template <int D>
 LQ_HD M3 lq_gauss_site(const cx* LQ_RESTRICT U, const cx* E, const LqGeom& g, const Site<D>& x) {
   M3 acc = m3_zero();
-  lq_i64 p = lq_phys(g, x.s);
+  lq_i64 p = lq_slot<D>(g, x);
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     acc = m3_add(acc, lq_adjoint_to_matrix(lq_load_e(E, g, i, p)));
     Site<D> xm = lq_dn<D>(g, x, i);
-    lq_i64 pm = lq_phys(g, xm.s);
+    lq_i64 pm = lq_slot<D>(g, xm);
     M3 u = lq_load_link(U, g, i, pm);
     M3 em = lq_adjoint_to_matrix(lq_load_e(E, g, i, pm));
     M3 t = m3_mul_dn(u, em);  // U^+ E
@@ -422,9 +422,8 @@ struct KGaussField {
   LQ_HD void operator()(lq_i64 n) const {
     Site<D> x = lq_site<D>(g, n);
     M3 m = lq_gauss_site<D>(U, E, g, x);
-    lq_i64 p = lq_phys(g, x.s);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) G[k * g.pitch + p] = m.e[k];
+    lq_i64 p = lq_slot<D>(g, x);
+    lq_store_g(G, p, m);
   }
 };
 template <int D>
@@ -434,10 +433,8 @@ struct KGaussToAos {
   double* aos;
   LQ_HD void operator()(lq_i64 n) const {
     Site<D> x = lq_site<D>(g, n);
-    lq_i64 p = lq_phys(g, x.s);
-    M3 m;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) m.e[k] = G[k * g.pitch + p];
+    lq_i64 p = lq_slot<D>(g, x);
+    M3 m = lq_load_g(G, p);
     lq_m3_to_aos(aos + lq_local_index<D>(g, x) * 18, m);
   }
 };
@@ -449,10 +446,8 @@ struct KGaussDiv {
   const cx* G;
   LQ_HD void operator()(lq_i64 n, double* v) const {
     Site<D> x = lq_site<D>(g, n);
-    lq_i64 p = lq_phys(g, x.s);
-    M3 m;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) m.e[k] = G[k * g.pitch + p];
+    lq_i64 p = lq_slot<D>(g, x);
+    M3 m = lq_load_g(G, p);
     cx tr[8];
     lq_trace_gen(m, tr);
     double re = 0.0, im = 0.0;
@@ -479,16 +474,11 @@ struct KGaussProjectStep {
     int dir;
     if (!lq_decode_link<D>(g, i, n, dir)) return;
     Site<D> x = lq_site<D>(g, n);
-    lq_i64 p = lq_phys(g, x.s);
+    lq_i64 p = lq_slot<D>(g, x);
     Site<D> xp = lq_up<D>(g, x, dir);
-    lq_i64 pp = lq_phys(g, xp.s);
+    lq_i64 pp = lq_slot<D>(g, xp);
     M3 u = lq_load_link(U, g, dir, p);
-    M3 gx, gp;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      gx.e[k] = G[k * g.pitch + p];
-      gp.e[k] = G[k * g.pitch + pp];
-    }
+    M3 gx = lq_load_g(G, p), gp = lq_load_g(G, pp);
     M3 t = m3_mul_nd(m3_mul_nn(u, gx), u);
     M3 m = m3_mul_nn(t, gp);
     m = m3_scale(m3_sub(m, gx), 0.12);
@@ -513,7 +503,7 @@ struct KHeatBath {  // HeatBathSweep, heat_bath.rs:73-123
   uint64_t seed, counter;
   LQ_HD void operator()(lq_i64 n) const {
     Site<D> x = lq_site_eo<D>(g, n, parity);
-    lq_i64 p = lq_phys(g, x.s);
+    lq_i64 p = lq_slot<D>(g, x);
     M3 a = lq_staple_sum<D>(U, g, x, dir);
     M3 u = lq_load_link_rw(U, g, dir, p);
     LqStream rng(seed, counter, (uint64_t)(lq_global_index<D>(g, x) * D + dir));
@@ -527,7 +517,7 @@ struct KOverrelax {  // OverrelaxationSweep{Rotation,Reverse}, overrelaxation.rs
   int dir, parity, kind;
   LQ_HD void operator()(lq_i64 n) const {
     Site<D> x = lq_site_eo<D>(g, n, parity);
-    lq_i64 p = lq_phys(g, x.s);
+    lq_i64 p = lq_slot<D>(g, x);
     M3 a = lq_staple_sum<D>(U, g, x, dir);
     M3 u = lq_load_link_rw(U, g, dir, p);
     lq_store_link(U, g, dir, p, lq_overrelax_link(u, a, kind));
@@ -543,7 +533,7 @@ struct KMetropolis {  // MetropolisHastingsSweep, metropolis_hastings_sweep.rs:1
   uint64_t seed, counter;
   LQ_HD void operator()(lq_i64 n, double* v) const {
     Site<D> x = lq_site_eo<D>(g, n, parity);
-    lq_i64 p = lq_phys(g, x.s);
+    lq_i64 p = lq_slot<D>(g, x);
     M3 old = lq_load_link_rw(U, g, dir, p);
     LqStream rng(seed, counter, (uint64_t)(lq_global_index<D>(g, x) * D + dir));
     M3 prop = lq_metropolis_proposal(old, n_update, spread, rng, flags);
@@ -589,7 +579,7 @@ struct KHaloPack {
     lq_i64 pl = i / nface;
     lq_i64 n = i - pl * nface;
     if (pl >= planes) return;
-    buf[i] = F[pl * g.pitch + lq_phys(g, lq_face_site<D>(g, hd, xh, n))];
+    buf[i] = F[lq_addr(lq_slot_s(g, lq_face_site<D>(g, hd, xh, n)), planes, (int)pl)];
   }
 };
 template <int D>
@@ -603,6 +593,6 @@ struct KHaloUnpack {
     lq_i64 pl = i / nface;
     lq_i64 n = i - pl * nface;
     if (pl >= planes) return;
-    F[pl * g.pitch + lq_phys(g, lq_face_site<D>(g, hd, xh, n))] = buf[i];
+    F[lq_addr(lq_slot_s(g, lq_face_site<D>(g, hd, xh, n)), planes, (int)pl)] = buf[i];
   }
 };

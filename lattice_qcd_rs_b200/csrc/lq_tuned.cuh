@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   const lq_i64 n = (lq_i64)blockIdx.x * SITES + (threadIdx.x - mu * SITES);
   if (n >= g.vol) return;
   const Site<4> st = lq_tuned_site<MAP>(g, n);
-  const lq_i64 p = lq_phys(g, st.s);
+  const lq_i64 p = lq_slot<4>(g, st);
   M3 a = lq_staple_sum<4>(U, g, st, mu);
   M3 u = lq_load_link(U, g, mu, p);
   M3 w = m3_mul_nn(u, a);
@@ -61,12 +61,12 @@ __global__ void __launch_bounds__(384, MINB)
   M3 acc = m3_zero();
   if (live) {
     st = lq_tuned_site<MAP>(g, n);
-    p = lq_phys(g, st.s);
+    p = lq_slot<4>(g, st);
     const Site<4> xpm = lq_up<4>(g, st, mu);
     {
       const Site<4> xpn = lq_up<4>(g, st, nu);
-      M3 a = lq_load_link(U, g, nu, lq_phys(g, xpm.s));
-      M3 b = lq_load_link(U, g, mu, lq_phys(g, xpn.s));
+      M3 a = lq_load_link(U, g, nu, lq_slot<4>(g, xpm));
+      M3 b = lq_load_link(U, g, mu, lq_slot<4>(g, xpn));
       M3 t = m3_mul_nd(a, b);
       M3 c = lq_load_link(U, g, nu, p);
       m3_fma_nd(acc, t, c);
@@ -74,10 +74,10 @@ __global__ void __launch_bounds__(384, MINB)
     {
       const Site<4> xmn = lq_dn<4>(g, st, nu);
       const Site<4> xpmmn = lq_dn<4>(g, xpm, nu);
-      M3 a = lq_load_link(U, g, mu, lq_phys(g, xmn.s));
-      M3 b = lq_load_link(U, g, nu, lq_phys(g, xpmmn.s));
+      M3 a = lq_load_link(U, g, mu, lq_slot<4>(g, xmn));
+      M3 b = lq_load_link(U, g, nu, lq_slot<4>(g, xpmmn));
       M3 t = m3_mul_nn(a, b);
-      M3 c = lq_load_link(U, g, nu, lq_phys(g, xmn.s));
+      M3 c = lq_load_link(U, g, nu, lq_slot<4>(g, xmn));
       m3_fma_dn(acc, t, c);
     }
     if (slot > 0) {
@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   const lq_i64 n = (lq_i64)blockIdx.x * SITES + (threadIdx.x - mu * SITES);
   if (n >= g.vol) return;
   const Site<4> st = lq_tuned_site<MAP>(g, n);
-  const lq_i64 p = lq_phys(g, st.s);
+  const lq_i64 p = lq_slot<4>(g, st);
   const Site<4> xpm = lq_up<4>(g, st, mu);
-  const lq_i64 ppm = lq_phys(g, xpm.s);
+  const lq_i64 ppm = lq_slot<4>(g, xpm);
   M3 acc = m3_zero();
 #pragma unroll 1
   for (int j = 1; j < 4; ++j) {
@@ -129,17 +129,17 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     const Site<4> xpn = lq_up<4>(g, st, nu);
     const Site<4> xmn = lq_dn<4>(g, st, nu);
     const Site<4> xpmmn = lq_dn<4>(g, xpm, nu);
-    const lq_i64 pmn = lq_phys(g, xmn.s);
+    const lq_i64 pmn = lq_slot<4>(g, xmn);
     {
       M3 a = lq_load_link(U, g, nu, ppm);
-      M3 b = lq_load_link(U, g, mu, lq_phys(g, xpn.s));
+      M3 b = lq_load_link(U, g, mu, lq_slot<4>(g, xpn));
       M3 t = m3_mul_nd(a, b);
       M3 c = lq_load_link(U, g, nu, p);
       m3_fma_nd(acc, t, c);
     }
     {
       M3 a = lq_load_link(U, g, mu, pmn);
-      M3 b = lq_load_link(U, g, nu, lq_phys(g, xpmmn.s));
+      M3 b = lq_load_link(U, g, nu, lq_slot<4>(g, xpmmn));
       M3 t = m3_mul_nn(a, b);
       M3 c = lq_load_link(U, g, nu, pmn);
       m3_fma_dn(acc, t, c);
@@ -156,6 +156,120 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   }
   lq_store_e(E, g, mu, p, e);
   if (FUSED) lq_store_link(Unew, g, mu, p, lq_link_update<4>(u, e, dt_u, c_u, 0));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// V4: lean index arithmetic.  One thread per link, a warp = 32 consecutive site slots (one chunk of the chunked-SoA
+// layout when ext0 is a multiple of 32) of one direction.  All neighbour slots are p + (sum of per-direction
+// deltas): the eight deltas are computed once per thread, every matrix is one 32-bit element index -> IMAD.WIDE ->
+// nine LDG.128 with immediate offsets.  The loop over nu is not unrolled (instruction-cache resident body).
+__device__ __forceinline__ int lq_sel4(int d, int a0, int a1, int a2, int a3) {
+  return d == 0 ? a0 : d == 1 ? a1 : d == 2 ? a2 : a3;
+}
+__device__ __forceinline__ M3 lq_ld36(const cx* __restrict__ U, int slot, int dir) {
+  const int e = ((slot >> 5) * 36 + dir * 9) * 32 + (slot & 31);
+  const cx* b = U + e;
+  M3 r;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.e[k] = __ldg(b + k * 32);
+  return r;
+}
+template <int BLOCK, int MINB, int FUSED>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_md4_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef, double dt_e,
+                  double dt_u, double c_u, int nkick) {
+  constexpr int SITES = BLOCK / 4;
+  const int mu = threadIdx.x / SITES;
+  const int n = blockIdx.x * SITES + (threadIdx.x - mu * SITES);
+  if (n >= (int)g.vol) return;
+  // site decode (row walk, even x0 first)
+  const int e0 = g.ext[0], ne0 = g.ne0;
+  int row = n / e0;
+  const int lane = n - row * e0;
+  const int x0 = lane < ne0 ? 2 * lane : 2 * (lane - ne0) + 1;
+  int q = row / g.ext[1];
+  const int x1 = row - q * g.ext[1] + g.ghost[1];
+  row = q;
+  q = row / g.ext[2];
+  const int x2 = row - q * g.ext[2] + g.ghost[2];
+  const int x3 = q + g.ghost[3];
+  const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
+  const int p = x1 * s1 + x2 * s2 + x3 * s3 + (x0 & 1) * ne0 + (x0 >> 1);
+  // slot deltas of the eight neighbours
+  const int x0p = x0 + 1 < e0 ? x0 + 1 : 0, x0m = x0 > 0 ? x0 - 1 : e0 - 1;
+  const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
+  const int up0 = (x0p & 1) * ne0 + (x0p >> 1) - sl0, dn0 = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
+  const int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
+  const int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
+  const int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
+  const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
+  // E early: its latency hides behind the staples
+  const int ee = ((p >> 5) * 16 + mu * 4) * 32 + (p & 31);
+  cx ev[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ev[k] = E[ee + k * 32];
+  M3 acc = m3_zero();
+#pragma unroll 1
+  for (int j = 1; j < 4; ++j) {
+    const int nu = (mu + j) & 3;
+    const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
+    {  // up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)
+      M3 a = lq_ld36(U, pm, nu);
+      M3 b = lq_ld36(U, p + upn, mu);
+      M3 t = m3_mul_nd(a, b);
+      M3 c = lq_ld36(U, p, nu);
+      m3_fma_nd(acc, t, c);
+    }
+    {  // down:  (U_mu(x-nu) U_nu(x+mu-nu))^+ U_nu(x-nu)
+      M3 a = lq_ld36(U, p + dnn, mu);
+      M3 b = lq_ld36(U, pm + dnn, nu);
+      M3 t = m3_mul_nn(a, b);
+      M3 c = lq_ld36(U, p + dnn, nu);
+      m3_fma_dn(acc, t, c);
+    }
+  }
+  M3 u = lq_ld36(U, p, mu);
+  M3 w = m3_mul_nn(u, acc);
+  cx tr[8];
+  lq_trace_gen(w, tr);
+  A8 e;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e.e[2 * k] = ev[k].x;
+    e.e[2 * k + 1] = ev[k].y;
+  }
+  for (int kk = 0; kk < nkick; ++kk) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) E[ee + k * 32] = cmk(e.e[2 * k], e.e[2 * k + 1]);
+  if (FUSED) {
+    M3 un = lq_link_update<4>(u, e, dt_u, c_u, 0);
+    cx* b = Unew + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) b[k * 32] = un.e[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launchers used by lq_capi.cu (D = 4; 32-bit element indices: fields below 2^31 elements, else the generic path)
+static inline bool lq_tuned_ok(const LqGeom& g) {
+  return g.D == 4 && g.nchunk * 32 * 36 < ((lq_i64)1 << 31) && g.vol < ((lq_i64)1 << 31);
+}
+static inline cudaError_t lq_tuned_efield_step(cudaStream_t st, const LqGeom& g, const cx* U, cx* E, double coef, double dt,
+                                               int nkick) {
+  constexpr int BLOCK = 128;
+  lq_md4_kernel<BLOCK, 3, 0><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, nullptr, E, coef, dt,
+                                                                                                0.0, 0.0, nkick);
+  return cudaGetLastError();
+}
+static inline cudaError_t lq_tuned_efield_link_step(cudaStream_t st, const LqGeom& g, const cx* U, cx* Unew, cx* E,
+                                                    double coef, double dt_e, double dt_u, double c_u, int nkick) {
+  constexpr int BLOCK = 128;
+  lq_md4_kernel<BLOCK, 3, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e,
+                                                                                                dt_u, c_u, nkick);
+  return cudaGetLastError();
 }
 
 #endif  // !LQ_HOST_EMU

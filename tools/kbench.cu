@@ -82,7 +82,7 @@ int main(int argc, char** argv) {
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device %s, %d SMs, L=%d, vol=%lld, links=%lld\n", prop.name, prop.multiProcessorCount, L, g.vol, g.vol * 4);
 
-  size_t ub = (size_t)g.pitch * 36 * sizeof(cx), eb = (size_t)g.pitch * 16 * sizeof(cx);
+  size_t ub = (size_t)g.nchunk * 32 * 36 * sizeof(cx), eb = (size_t)g.nchunk * 32 * 16 * sizeof(cx);
   cx *U, *U2, *E, *E0, *Uref, *Eref;
   CK(cudaMalloc(&U, ub)); CK(cudaMalloc(&U2, ub)); CK(cudaMalloc(&Uref, ub));
   CK(cudaMalloc(&E, eb)); CK(cudaMalloc(&E0, eb)); CK(cudaMalloc(&Eref, eb));
@@ -109,7 +109,7 @@ int main(int argc, char** argv) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     double fl = 2.0 * 8 * iters * 148.0 * 8 * 256;
     printf("FP64 FMA peak: %.2f TFLOP/s (%.3f ms)\n", fl / ms / 1e9, ms);
-    lq_i64 n = (lq_i64)g.pitch * 36;
+    lq_i64 n = (lq_i64)g.nchunk * 32 * 36;
     copy_k<<<148 * 16, 256>>>(U, U2, n);
     CK(cudaEventRecord(e0));
     for (int r = 0; r < 5; ++r) copy_k<<<148 * 16, 256>>>(U, U2, n);
@@ -196,6 +196,21 @@ int main(int argc, char** argv) {
   V3(256, 1, 0, g, "row");
   V3(256, 2, 0, g, "row");
   V3(512, 1, 1, tiled(32, 2, 2, 1), "tile32x2x2x1");
+#define V4(BLOCK, MINB)                                                                                            \
+  vs.push_back({std::string("v4 lean nu-loop block=" #BLOCK " minb=" #MINB),                                        \
+                [&] {                                                                                               \
+                  lq_md4_kernel<BLOCK, MINB, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>(      \
+                      g, U, U2, E, coef, dt / 2, dt, c_u, 2);                                                       \
+                  CK(cudaGetLastError());                                                                           \
+                },                                                                                                  \
+                (const void*)lq_md4_kernel<BLOCK, MINB, 1>, BLOCK})
+  V4(128, 1);
+  V4(128, 2);
+  V4(128, 3);
+  V4(128, 4);
+  V4(256, 1);
+  V4(256, 2);
+  V4(512, 1);
 #define V2(MINB, MAP, GEOM, LABEL)                                                                           \
   vs.push_back({std::string("v2 nu-split block=384 minb=" #MINB " ") + LABEL,                                 \
                 [&, gg = GEOM] {                                                                              \
