@@ -111,6 +111,7 @@ struct lq_ctx {
   double* d_result;
   double* h_result;
   bool halo_ok[3];
+  bool g_valid;  // the Gauss field in G matches the current (U, E)
   lq_comm comm;
   bool has_comm;
   // optional per-kernel-class CUDA-event timing (lq_profile_*)
@@ -496,11 +497,13 @@ int lq_is_decomposed(const lq_ctx* c, int dir) { return (c && dir >= 0 && dir < 
 static int links_from_device_aos(lq_ctx* c, const double* d_aos) {
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinksFromAos<DD>{c->g, d_aos, c->U}))));
   c->halo_ok[0] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 static int efield_from_device_aos(lq_ctx* c, const double* d_aos) {
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KEFromAos<DD>{c->g, d_aos, c->E}))));
   c->halo_ok[1] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 static int links_to_device_aos(lq_ctx* c, double* d_aos) {
@@ -580,11 +583,13 @@ int lq_links_set_cold(lq_ctx* c) {
   LQ_GUARD(c);
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinksCold<DD>{c->g, c->U}))));
   c->halo_ok[0] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 int lq_efield_set_zero(lq_ctx* c) {
   if (!c) return LQ_E_BADARG;
   LQ_GUARD(c);
+  c->g_valid = false;
   c->halo_ok[1] = true;  // zero everywhere, ghosts included
   return rt_memset(c->E, 0, c->e_bytes(), c->stream);
 }
@@ -593,6 +598,7 @@ int lq_links_set_random(lq_ctx* c, uint64_t seed, uint64_t counter) {
   LQ_GUARD(c);
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinksRandom<DD>{c->g, c->U, seed, counter}))));
   c->halo_ok[0] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 
@@ -682,17 +688,20 @@ static int efield_step(lq_ctx* c, double dt, int nkick) {
     LQ_CHECK(lq_tuned_efield_step(c->stream, c->g, c->U, c->E, force_coef(c), dt, nkick));
     c->launches++;
     c->halo_ok[1] = false;
+  c->g_valid = false;
     return LQ_OK;
   }
 #endif
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KEfieldStep<DD>{c->g, c->U, c->E, force_coef(c), dt, nkick}))));
   c->halo_ok[1] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 static int link_step(lq_ctx* c, const cx* Uin, cx* Uout, double dt, int use_exp) {
   ProfScope ps(c, LQ_PROF_LINK_STEP);
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinkStep<DD>{c->g, Uin, Uout, c->E, dt, link_coef(c), use_exp}))));
   c->halo_ok[0] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 // E += nkick * (dt_e F[U]);  U <- step(U, E_new, dt_u)  in one kernel (second link buffer, then swap)
@@ -716,7 +725,9 @@ static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u) {
   c->U = c->U2;
   c->U2 = t;
   c->halo_ok[0] = false;
+  c->g_valid = false;
   c->halo_ok[1] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 int lq_efield_step(lq_ctx* c, double dt) {
@@ -741,6 +752,7 @@ int lq_integrate(lq_ctx* c, int kind, double dt) {
       c->U = c->U2;
       c->U2 = t;
       c->halo_ok[0] = false;
+  c->g_valid = false;
       c->t += 1;
       return LQ_OK;
     }
@@ -795,6 +807,7 @@ int lq_reunitarize(lq_ctx* c) {
   LQ_GUARD(c);
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KReunitarize<DD>{c->g, c->U}))));
   c->halo_ok[0] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 
@@ -804,15 +817,18 @@ int lq_momenta_refresh(lq_ctx* c, uint64_t seed, uint64_t counter, double sigma)
   LQ_GUARD(c);
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KMomentaRefresh<DD>{c->g, c->E, seed, counter, sigma}))));
   c->halo_ok[1] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 static int gauss_field(lq_ctx* c) {
+  if (c->g_valid && c->G) return LQ_OK;  // E and U unchanged since the last evaluation (e.g. residual check -> next step)
   LQ_TRY(ensure_buf(&c->G, c->g_bytes(), c));
   LQ_TRY(ensure_halo(c, 0));
   LQ_TRY(ensure_halo(c, 1));
   ProfScope ps(c, LQ_PROF_GAUSS_FIELD);
   LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussField<DD>{c->g, c->U, c->E, c->G}))));
   c->halo_ok[2] = false;
+  c->g_valid = true;
   return LQ_OK;
 }
 int lq_gauss_field(lq_ctx* c, double* aos_out, int64_t n_sites) {
@@ -848,6 +864,7 @@ int lq_gauss_project_step(lq_ctx* c) {
   c->E = c->E2;
   c->E2 = t;
   c->halo_ok[1] = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 int lq_gauss_project(lq_ctx* c, int64_t max_steps, int64_t* steps_out) {
@@ -890,6 +907,7 @@ int lq_sweep_heatbath(lq_ctx* c, uint64_t seed, uint64_t counter, double couplin
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2,
                                      KHeatBath<DD>{c->g, c->U, d, p, c->flags, c->beta * coupling_scale, seed, counter}))));
       c->halo_ok[0] = false;
+  c->g_valid = false;
     }
   return LQ_OK;
 }
@@ -903,6 +921,7 @@ int lq_sweep_overrelax(lq_ctx* c, int kind) {
       ProfScope ps(c, LQ_PROF_OVERRELAX);
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2, KOverrelax<DD>{c->g, c->U, d, p, kind}))));
       c->halo_ok[0] = false;
+  c->g_valid = false;
     }
   return LQ_OK;
 }
@@ -922,6 +941,7 @@ int lq_sweep_metropolis(lq_ctx* c, uint64_t seed, uint64_t counter, double sprea
       acc[0] += c->h_result[0];
       acc[1] += c->h_result[1];
       c->halo_ok[0] = false;
+  c->g_valid = false;
     }
   LQ_TRY(global_sum(c, acc, 2));
   if (n_accept) *n_accept = (int64_t)(acc[0] + 0.5);
@@ -949,6 +969,8 @@ int lq_restore(lq_ctx* c) {
   LQ_TRY(rt_copy(c->E, c->snapE, c->e_bytes(), D2D, c->stream));
   c->t = c->snap_t;
   c->halo_ok[0] = c->halo_ok[1] = false;
+  c->g_valid = false;
+  c->g_valid = false;
   return LQ_OK;
 }
 int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint64_t counter, double sigma,
@@ -975,6 +997,7 @@ int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint
   if (!ok) {
     LQ_TRY(rt_copy(c->U, c->snapU, c->u_bytes(), D2D, c->stream));
     c->halo_ok[0] = false;
+  c->g_valid = false;
     c->t = t0;
   }
   if (h_old) *h_old = h0;

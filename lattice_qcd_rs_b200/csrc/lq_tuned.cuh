@@ -174,7 +174,9 @@ __device__ __forceinline__ M3 lq_ld36(const cx* __restrict__ U, int slot, int di
   for (int k = 0; k < 9; ++k) r.e[k] = __ldg(b + k * 32);
   return r;
 }
-template <int BLOCK, int MINB, int FUSED>
+// FLAGS: 1 = visit nu so that direction 3 (first touched from DRAM by most blocks) comes last, 2 = streaming
+// (evict-first) accesses for E and U', 4 = FAKE neighbours (perfect-locality bound, kbench only: wrong results)
+template <int BLOCK, int MINB, int FUSED, int FLAGS = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
     lq_md4_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef, double dt_e,
                   double dt_u, double c_u, int nkick) {
@@ -199,19 +201,38 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   const int x0p = x0 + 1 < e0 ? x0 + 1 : 0, x0m = x0 > 0 ? x0 - 1 : e0 - 1;
   const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
   const int up0 = (x0p & 1) * ne0 + (x0p >> 1) - sl0, dn0 = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
-  const int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
-  const int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
-  const int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
+  int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
+  int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
+  int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
+  if (FLAGS & 4) up1 = up2 = up3 = dn1 = dn2 = dn3 = 0;
+  if (FLAGS & 8) {
+    // L2 prefetch for the blocks one wave ahead: the link chunk that will be their cold (+x3) neighbour row and
+    // their own E chunk.  One 128-byte line per thread.
+    constexpr int PFD = 640;
+    const int nch = (int)g.nchunk;
+    int cu = (p >> 5) + (s3 >> 5) + PFD * (SITES / 32);
+    cu -= cu >= nch ? nch : 0;
+    cu -= cu >= nch ? nch : 0;
+    int ce = (p >> 5) + PFD * (SITES / 32);
+    ce -= ce >= nch ? nch : 0;
+    const char* pu = (const char*)(U + (lq_i64)cu * 36 * 32);
+    const char* pe = (const char*)(E + (lq_i64)ce * 16 * 32);
+    const int t = threadIdx.x;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + t * 128));
+    if (t < 144 - BLOCK) asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + (BLOCK + t) * 128));
+    if (t < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + t * 128));
+  }
   const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
   // E early: its latency hides behind the staples
   const int ee = ((p >> 5) * 16 + mu * 4) * 32 + (p & 31);
   cx ev[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) ev[k] = E[ee + k * 32];
+  for (int k = 0; k < 4; ++k) ev[k] = (FLAGS & 2) ? __ldcs(E + ee + k * 32) : E[ee + k * 32];
   M3 acc = m3_zero();
 #pragma unroll 1
   for (int j = 1; j < 4; ++j) {
-    const int nu = (mu + j) & 3;
+    // default: nu = mu+1, mu+2, mu+3 (mod 4); FLAGS&1: nu ascending with the own direction skipped (3 last)
+    const int nu = (FLAGS & 1) ? (j - 1 + (j - 1 >= mu ? 1 : 0)) : ((mu + j) & 3);
     const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
     {  // up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)
       M3 a = lq_ld36(U, pm, nu);
@@ -243,12 +264,18 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) E[ee + k * 32] = cmk(e.e[2 * k], e.e[2 * k + 1]);
+  for (int k = 0; k < 4; ++k) {
+    if (FLAGS & 2) __stcs(E + ee + k * 32, cmk(e.e[2 * k], e.e[2 * k + 1]));
+    else E[ee + k * 32] = cmk(e.e[2 * k], e.e[2 * k + 1]);
+  }
   if (FUSED) {
     M3 un = lq_link_update<4>(u, e, dt_u, c_u, 0);
     cx* b = Unew + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) b[k * 32] = un.e[k];
+    for (int k = 0; k < 9; ++k) {
+      if (FLAGS & 2) __stcs(b + k * 32, un.e[k]);
+      else b[k * 32] = un.e[k];
+    }
   }
 }
 
@@ -260,14 +287,14 @@ static inline bool lq_tuned_ok(const LqGeom& g) {
 static inline cudaError_t lq_tuned_efield_step(cudaStream_t st, const LqGeom& g, const cx* U, cx* E, double coef, double dt,
                                                int nkick) {
   constexpr int BLOCK = 128;
-  lq_md4_kernel<BLOCK, 3, 0><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, nullptr, E, coef, dt,
+  lq_md4_kernel<BLOCK, 3, 0, 2><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, nullptr, E, coef, dt,
                                                                                                 0.0, 0.0, nkick);
   return cudaGetLastError();
 }
 static inline cudaError_t lq_tuned_efield_link_step(cudaStream_t st, const LqGeom& g, const cx* U, cx* Unew, cx* E,
                                                     double coef, double dt_e, double dt_u, double c_u, int nkick) {
   constexpr int BLOCK = 128;
-  lq_md4_kernel<BLOCK, 3, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e,
+  lq_md4_kernel<BLOCK, 3, 1, 2><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e,
                                                                                                 dt_u, c_u, nkick);
   return cudaGetLastError();
 }

@@ -204,13 +204,25 @@ int main(int argc, char** argv) {
                   CK(cudaGetLastError());                                                                           \
                 },                                                                                                  \
                 (const void*)lq_md4_kernel<BLOCK, MINB, 1>, BLOCK})
-  V4(128, 1);
-  V4(128, 2);
   V4(128, 3);
-  V4(128, 4);
-  V4(256, 1);
-  V4(256, 2);
-  V4(512, 1);
+  V4(64, 6);
+  V4(64, 7);
+  V4(192, 2);
+#define V4F(BLOCK, MINB, FLAGS, CARVE)                                                                             \
+  vs.push_back({std::string("v4 block=" #BLOCK " minb=" #MINB " flags=" #FLAGS " carveout=" #CARVE),              \
+                [&] {                                                                                               \
+                  if (CARVE >= 0)                                                                                   \
+                    cudaFuncSetAttribute(lq_md4_kernel<BLOCK, MINB, 1, FLAGS>,                                      \
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, CARVE);                   \
+                  lq_md4_kernel<BLOCK, MINB, 1, FLAGS><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>( \
+                      g, U, U2, E, coef, dt / 2, dt, c_u, 2);                                                       \
+                  CK(cudaGetLastError());                                                                           \
+                },                                                                                                  \
+                (const void*)lq_md4_kernel<BLOCK, MINB, 1, FLAGS>, BLOCK})
+  V4F(128, 3, 2, -1);
+  V4F(128, 3, 8, -1);
+  V4F(128, 3, 10, -1);
+  V4F(128, 3, 4, -1);
 #define V2(MINB, MAP, GEOM, LABEL)                                                                           \
   vs.push_back({std::string("v2 nu-split block=384 minb=" #MINB " ") + LABEL,                                 \
                 [&, gg = GEOM] {                                                                              \
