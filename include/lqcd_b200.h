@@ -67,6 +67,10 @@ int lq_ctx_create(lq_ctx** out, int device, int D, const int64_t* extent, double
  * and filled through lq_halo_* (host-staged or peer-mapped transport supplied by the caller's plumbing). */
 int lq_ctx_create_dist(lq_ctx** out, int device, int D, const int64_t* global_extent, const int* proc_grid,
                        const int* rank_coord, double lattice_spacing_a, double beta, double CA);
+/* `Clone` of a device-resident state (SimulationStateSynchronous: Clone, state.rs:292-295; every integrator call
+ * returns a NEW state, symplectic_euler_rayon.rs:245-251): same lattice / beta / flags / t, links and E-field
+ * copied device to device.  Snapshots and profiling state are not copied. */
+int lq_ctx_clone(const lq_ctx* src, lq_ctx** out);
 int lq_ctx_destroy(lq_ctx*);
 int lq_set_flags(lq_ctx*, int flags);
 int lq_get_flags(lq_ctx*, int* flags);

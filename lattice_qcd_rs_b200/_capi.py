@@ -50,6 +50,7 @@ SYMBOLS = {
     "lq_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _i64p, C.c_double, C.c_double, C.c_double]),
     "lq_ctx_create_dist": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _i64p, _ip, _ip, C.c_double, C.c_double,
                                      C.c_double]),
+    "lq_ctx_clone": (C.c_int, [_vp, C.POINTER(_vp)]),
     "lq_ctx_destroy": (C.c_int, [_vp]),
     "lq_set_flags": (C.c_int, [_vp, C.c_int]),
     "lq_get_flags": (C.c_int, [_vp, _ip]),
@@ -183,6 +184,15 @@ class Context:
             if rc == -3:
                 detail = self.lib.lq_last_cuda_error().decode()
             raise LqError(rc, where, detail)
+
+    def clone(self):
+        """Device-to-device copy of this context (lattice, beta, flags, t, links, E-field)."""
+        h = _vp()
+        self._check(self.lib.lq_ctx_clone(self._h, C.byref(h)), "lq_ctx_clone")
+        new = object.__new__(Context)
+        new.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_h"})
+        new._h = h
+        return new
 
     def close(self):
         if getattr(self, "_h", None):

@@ -408,6 +408,36 @@ int lq_ctx_create_dist(lq_ctx** out, int device, int D, const int64_t* gext, con
   if (!proc_grid || !coord) return LQ_E_BADARG;
   return ctx_create_common(out, device, D, gext, proc_grid, coord, a, beta, CA);
 }
+int lq_ctx_clone(const lq_ctx* src, lq_ctx** out) {
+  if (!src || !out) return LQ_E_BADARG;
+  *out = nullptr;
+  int64_t gext[LQ_MAXD];
+  int coord[LQ_MAXD];
+  for (int d = 0; d < LQ_MAXD; ++d) {
+    gext[d] = src->g.gext[d];
+    coord[d] = src->g.ext[d] > 0 ? src->g.goff[d] / src->g.ext[d] : 0;
+  }
+  lq_ctx* c = nullptr;
+  LQ_TRY(ctx_create_common(&c, src->device, src->g.D, gext, src->nproc, coord, src->a, src->beta, src->CA));
+  LQ_GUARD(c);
+  c->flags = src->flags;
+  c->t = src->t;
+  c->comm = src->comm;
+  c->has_comm = src->has_comm;
+  // order the copy after everything already queued on the source stream
+  int rc = rt_sync(src->stream);
+  if (!rc) rc = rt_copy(c->U, src->U, c->u_bytes(), D2D, c->stream);
+  if (!rc) rc = rt_copy(c->E, src->E, c->e_bytes(), D2D, c->stream);
+  if (!rc) rc = rt_sync(c->stream);
+  if (rc) {
+    lq_ctx_destroy(c);
+    return rc;
+  }
+  c->halo_ok[0] = src->halo_ok[0];
+  c->halo_ok[1] = src->halo_ok[1];
+  *out = c;
+  return LQ_OK;
+}
 int lq_ctx_destroy(lq_ctx* c) {
   if (!c) return LQ_OK;
   LQ_GUARD(c);
