@@ -280,6 +280,101 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// V5: V4 with the loads software-pipelined by hand.  The staple sum is a stream of six (A, B, C) triples; the
+// loads of the next triple are issued before the two matrix products of the current one, so a warp hides its own
+// L2/DRAM latency behind ~430 DFMAs instead of relying on the two other warps of its scheduler (ncu of V4: 39 %
+// of the stall samples are long-scoreboard waits on the first DFMA that touches a freshly loaded matrix).
+// PIPE: 1 = prefetch A,B of the next half-stage; 2 = also fence the order with compiler barriers.
+#define LQ_CBAR() asm volatile("" ::: "memory")
+template <int BLOCK, int MINB, int FUSED, int PIPE = 1>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_md5_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef, double dt_e,
+                  double dt_u, double c_u, int nkick) {
+  constexpr int SITES = BLOCK / 4;
+  const int mu = threadIdx.x / SITES;
+  const int n = blockIdx.x * SITES + (threadIdx.x - mu * SITES);
+  if (n >= (int)g.vol) return;
+  const int e0 = g.ext[0], ne0 = g.ne0;
+  int row = n / e0;
+  const int lane = n - row * e0;
+  const int x0 = lane < ne0 ? 2 * lane : 2 * (lane - ne0) + 1;
+  int q = row / g.ext[1];
+  const int x1 = row - q * g.ext[1] + g.ghost[1];
+  row = q;
+  q = row / g.ext[2];
+  const int x2 = row - q * g.ext[2] + g.ghost[2];
+  const int x3 = q + g.ghost[3];
+  const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
+  const int p = x1 * s1 + x2 * s2 + x3 * s3 + (x0 & 1) * ne0 + (x0 >> 1);
+  const int x0p = x0 + 1 < e0 ? x0 + 1 : 0, x0m = x0 > 0 ? x0 - 1 : e0 - 1;
+  const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
+  const int up0 = (x0p & 1) * ne0 + (x0p >> 1) - sl0, dn0 = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
+  const int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
+  const int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
+  const int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
+  const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
+  const int ee = ((p >> 5) * 16 + mu * 4) * 32 + (p & 31);
+  M3 acc = m3_zero();
+  // prologue: A, B of the first up-staple
+  int nu = (mu + 1) & 3;
+  int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
+  M3 a = lq_ld36(U, pm, nu);
+  M3 b = lq_ld36(U, p + upn, mu);
+  cx ev[4];
+#pragma unroll 1
+  for (int j = 1; j < 4; ++j) {
+    M3 c = lq_ld36(U, p, nu);
+    M3 ad = lq_ld36(U, p + dnn, mu);
+    M3 bd = lq_ld36(U, pm + dnn, nu);
+    if (PIPE & 2) LQ_CBAR();
+    {  // up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)
+      M3 t = m3_mul_nd(a, b);
+      m3_fma_nd(acc, t, c);
+    }
+    if (PIPE & 2) LQ_CBAR();
+    c = lq_ld36(U, p + dnn, nu);
+    if (j < 3) {
+      nu = (mu + j + 1) & 3;
+      upn = lq_sel4(nu, up0, up1, up2, up3);
+      dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
+      a = lq_ld36(U, pm, nu);
+      b = lq_ld36(U, p + upn, mu);
+    } else {
+      a = lq_ld36(U, p, mu);  // the link itself, for U * A
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ev[k] = __ldcs(E + ee + k * 32);
+    }
+    if (PIPE & 2) LQ_CBAR();
+    {  // down:  (U_mu(x-nu) U_nu(x+mu-nu))^+ U_nu(x-nu)
+      M3 t = m3_mul_nn(ad, bd);
+      m3_fma_dn(acc, t, c);
+    }
+  }
+  const M3 u = a;
+  M3 w = m3_mul_nn(u, acc);
+  cx tr[8];
+  lq_trace_gen(w, tr);
+  A8 e;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e.e[2 * k] = ev[k].x;
+    e.e[2 * k + 1] = ev[k].y;
+  }
+  for (int kk = 0; kk < nkick; ++kk) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) __stcs(E + ee + k * 32, cmk(e.e[2 * k], e.e[2 * k + 1]));
+  if (FUSED) {
+    M3 un = lq_link_update<4>(u, e, dt_u, c_u, 0);
+    cx* bo = Unew + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) __stcs(bo + k * 32, un.e[k]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // launchers used by lq_capi.cu (D = 4; 32-bit element indices: fields below 2^31 elements, else the generic path)
 static inline bool lq_tuned_ok(const LqGeom& g) {
   return g.D == 4 && g.nchunk * 32 * 36 < ((lq_i64)1 << 31) && g.vol < ((lq_i64)1 << 31);

@@ -73,6 +73,7 @@ struct Variant {
 int main(int argc, char** argv) {
   int L = argc > 1 ? atoi(argv[1]) : 32;
   int reps = argc > 2 ? atoi(argv[2]) : 10;
+  const char* filter = argc > 3 ? argv[3] : "";  // run only the variants whose name contains this
   int64_t ext[4] = {L, L, L, L};
   LqGeom g;
   if (init_geom(g, 4, ext, nullptr, nullptr)) return 1;
@@ -223,6 +224,22 @@ int main(int argc, char** argv) {
   V4F(128, 3, 8, -1);
   V4F(128, 3, 10, -1);
   V4F(128, 3, 4, -1);
+#define V5(BLOCK, MINB, PIPE)                                                                                      \
+  vs.push_back({std::string("v5 pipelined block=" #BLOCK " minb=" #MINB " pipe=" #PIPE),                            \
+                [&] {                                                                                               \
+                  lq_md5_kernel<BLOCK, MINB, 1, PIPE><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>( \
+                      g, U, U2, E, coef, dt / 2, dt, c_u, 2);                                                       \
+                  CK(cudaGetLastError());                                                                           \
+                },                                                                                                  \
+                (const void*)lq_md5_kernel<BLOCK, MINB, 1, PIPE>, BLOCK})
+  V5(128, 3, 1);
+  V5(128, 3, 3);
+  V5(128, 2, 1);
+  V5(128, 2, 3);
+  V5(64, 6, 1);
+  V5(64, 6, 3);
+  V5(64, 4, 3);
+  V5(256, 1, 3);
 #define V2(MINB, MAP, GEOM, LABEL)                                                                           \
   vs.push_back({std::string("v2 nu-split block=384 minb=" #MINB " ") + LABEL,                                 \
                 [&, gg = GEOM] {                                                                              \
@@ -240,6 +257,7 @@ int main(int argc, char** argv) {
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   printf("%-52s %5s %4s %9s %9s %8s %10s %10s\n", "variant", "regs", "occ", "ms", "GB/s(alg)", "TF/s", "errE", "errU");
   for (auto& v : vs) {
+    if (filter[0] && v.name.find(filter) == std::string::npos && v.name.find("generic") == std::string::npos) continue;
     cudaFuncAttributes at;
     CK(cudaFuncGetAttributes(&at, v.func));
     int occ = 0;
