@@ -104,6 +104,7 @@ def cpu_sample(target_s=10.0, ext=8):
     trajectories (same beta, dt, MD steps) on a bounded ext^4 sample."""
     from oracle.oracle import Oracle
     o = Oracle(4, ext, a=SPACING, beta=BETA)
+    o.set_num_threads(os.cpu_count() or 1)
     U = o.links_random(SEED)
     reps, t0 = 0, time.perf_counter()
     while True:
@@ -126,6 +127,7 @@ def run_reference(args):
     from oracle.oracle import Oracle
     ext = 8
     o = Oracle(4, ext, a=SPACING, beta=BETA)
+    o.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core
     U = o.links_random(SEED)
     for k in range(args.warmup):
         U = o.normalize_links(o.hmc_trajectory(U, DT, MD_STEPS, SEED, k, literal=True)["U"])
@@ -150,6 +152,9 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # exactly ONE JSON line may reach stdout: NCCL/torch banners printed by native code go to stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product path has no CPU fallback"
@@ -237,16 +242,17 @@ def run_ours(args):
     hostU = torch.empty((nl_local, 18), dtype=torch.float64, pin_memory=True)
     hU = hostU.numpy()
     hU[:] = ctx.links_download()
-    e2e_state = {"n": 0}
+    e2e_state = {"n": 0, "gauss": 0}
 
     def e2e_step(i):
         ctx.links_upload(hU)
-        ctx.hmc_trajectory(DT, MD_STEPS, SEED, 5000 + e2e_state["n"])
+        e2e_state["gauss"] += ctx.hmc_trajectory(DT, MD_STEPS, SEED, 5000 + e2e_state["n"])["gauss_steps"]
         ctx.reunitarize()
         ctx.links_download(out=hU)
         e2e_state["n"] += 1
 
     e2e_step(0)
+    e2e_state["gauss"] = 0
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = MD_STEPS * nl_global * args.steps / (ms_e2e * 1e-3)
     bytes_links = nl_local * 18 * 8
@@ -275,7 +281,7 @@ def run_ours(args):
             tj = json.load(f)
         if tj.get("extent") == L:
             traffic = tj.get("dram_bytes_per_launch")
-    cpu, _, _ = cpu_sample()
+    cpu = cpu_sample()[0] if world == 1 else None  # reported on rank 0 at N = 1 only
     line = {
         "metric": "HMC link-updates/sec at 32^4 f64", "value": value, "unit": "link-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -301,12 +307,16 @@ def run_ours(args):
                      "fp64_note": "f64 FMA pipe is the co-limiter: ~3.1 kflop per 416 algorithmic bytes (7.5 flop/B)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "link-updates/s", "h2d_bytes_per_step": bytes_links,
-                "d2h_bytes_per_step": bytes_links + 64, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": bytes_links + 64, "ms_per_step": ms_e2e / args.steps,
+                "gauss_projection_steps_per_trajectory": e2e_state["gauss"] / max(args.steps, 1)},
         "gpu_launches": launches,
         "clocks": clocks,
         "sweeps": sweeps,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,0 +1,160 @@
+"""The reference's own tests for this path, replayed through the host-side mirror of its trait surface
+(lattice_qcd_rs_b200/state.py: LatticeStateDefault, LatticeStateEFSyncDefault, SymplecticEulerCuda,
+HybridMonteCarloDiagnostic, HeatBathSweep, ...).  Each test names the reference test / doc example it follows.
+
+Backends: "cuda" (gpu-marked: the product library) and "emu" (CPU CI: same kernel bodies compiled for the host,
+tests/emu.py -- test infrastructure).
+"""
+import numpy as np
+import pytest
+
+from lattice_qcd_rs_b200 import state as lq
+from oracle.oracle import Oracle
+from tests.conftest import SEED_RNG
+
+
+@pytest.fixture(params=["emu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def lib(request):
+    if request.param == "emu":
+        from tests import emu
+        return emu.lib()
+    import torch
+    assert torch.cuda.is_available(), "the gpu-marked tests need a CUDA device (no CPU fallback)"
+    return None  # state.py loads the CUDA library itself
+
+
+def test_lattice_and_state_errors(lib):
+    """LatticeCyclic::new (lattice.rs:190-201), LatticeStateNew::new size check (state.rs:784-786)."""
+    with pytest.raises(lq.LatticeInitializationError):
+        lq.LatticeCyclic(0.0, 4)
+    with pytest.raises(lq.LatticeInitializationError):
+        lq.LatticeCyclic(float("nan"), 4)
+    with pytest.raises(lq.LatticeInitializationError):
+        lq.LatticeCyclic(1.0, 1)
+    lat = lq.LatticeCyclic.new(1.0, 4)
+    assert lat.number_of_points() == 256 and lat.number_of_canonical_links_space() == 1024  # test_iterator_length
+    with pytest.raises(lq.StateInitializationError) as e:
+        lq.LatticeStateDefault.new(lat, 1.0, np.zeros((1023, 18)), lib=lib)
+    assert e.value.kind == "IncompatibleSize"
+    with pytest.raises(lq.StateInitializationError):
+        lq.LatticeStateDefault.new_cold(1.0, 1.0, 1, lib=lib)
+    st = lq.LatticeStateDefault.new_cold(1.0, 1.0, 4, lib=lib)
+    with pytest.raises(AssertionError):  # set_link_matrix panics on a wrong length, state.rs:808-815
+        st.set_link_matrix(np.zeros((10, 18)))
+    assert lq.MetropolisHastingsSweep.new(0, 0.1, lq.Rng(1)) is None       # metropolis_hastings_sweep.rs:73-80
+    assert lq.MetropolisHastingsSweep.new(1, 1.0, lq.Rng(1)) is None
+    with pytest.raises(lq.MultiIntegrationError):                            # state.rs:480-482
+        lq.LatticeStateEFSyncDefault.new_cold(1.0, 1.0, 4, lib=lib).simulate_symplectic_n(lq.SymplecticEulerCuda(), 0.1, 0)
+
+
+def test_sim_cold(lib):
+    """test_sim_cold, test/mod.rs:431-453: the cold state is an exact fixed point of sync->leap->leap->sync."""
+    size, number_of_pts, beta = 10.0, 4, 0.1
+    sim1 = lq.LatticeStateEFSyncDefault.new_cold(size, beta, number_of_pts, lib=lib)
+    integ = lq.SymplecticEulerCuda.new()
+    sim2 = sim1.simulate_to_leapfrog(integ, 0.1)
+    assert np.array_equal(sim1.e_field(), sim2.e_field()) and np.array_equal(sim1.link_matrix(), sim2.link_matrix())
+    sim3 = sim2.simulate_leap(integ, 0.1)
+    assert np.array_equal(sim2.e_field(), sim3.e_field()) and np.array_equal(sim2.link_matrix(), sim3.link_matrix())
+    sim4 = sim3.simulate_to_synchronous(integ, 0.1)
+    assert np.array_equal(sim3.e_field(), sim4.e_field()) and np.array_equal(sim3.link_matrix(), sim4.link_matrix())
+    assert sim4.t() == 2 and sim2.t() == 0  # t + 1 except sync_leap (symplectic_euler_rayon.rs:170-191)
+    assert abs(sim4.average_trace_plaquette() - 3.0) < 1e-15
+
+
+def test_sim_hamiltonian_and_gauss_law(lib):
+    """test_sim_hamiltonian_rayon / test_gauss_law_rayon, test/mod.rs:379-427."""
+    rng = lq.Rng.seed_from_u64(SEED_RNG)
+    state = lq.LatticeStateEFSyncDefault.new_determinist(100.0, 1.0, 6, rng, lib=lib)
+    h = state.hamiltonian_total()
+    state2 = state.simulate_sync(lq.SymplecticEulerCuda(), 1e-4)
+    assert abs(h - state2.hamiltonian_total()) < 0.01
+    g1 = state.gauss()
+    state3 = state.simulate_sync(lq.SymplecticEulerCuda(), 1e-6)
+    g2 = state3.gauss()
+    assert np.sqrt(((g1 - g2) ** 2).reshape(-1, 18).sum(axis=1)).max() < 1e-3
+    # the integrator returned NEW states: the original is untouched (state.rs:383-392 takes &self)
+    assert state.t() == 0 and state2.t() == 1
+    assert abs(state.hamiltonian_total() - h) == 0.0
+
+
+def test_leap_frog(lib):
+    """test_leap_frog, test/mod.rs:679-698: |dH| < 1e-5 after one leapfrog step dt = 0.01 (4^4, a = 1000, beta = 1)."""
+    rng = lq.Rng.seed_from_u64(0)
+    state = lq.LatticeStateEFSyncDefault.new_determinist(1000.0, 1.0, 4, rng, lib=lib)
+    h = state.hamiltonian_total()
+    leap = state.simulate_to_leapfrog(lq.SymplecticEulerCuda(), 0.01)
+    state2 = leap.simulate_to_synchronous(lq.SymplecticEulerCuda(), 0.01)
+    assert abs(h - state2.hamiltonian_total()) < 1e-5
+    state3 = state.simulate_using_leapfrog_n(lq.SymplecticEulerCuda(), 0.01, 1)
+    assert np.array_equal(state3.link_matrix(), state2.link_matrix())
+    state4 = state.simulate_using_leapfrog_n_auto(lq.SymplecticEulerCuda(), 0.01, 3)
+    assert state4.t() == 3 and abs(h - state4.hamiltonian_total()) < 1e-4
+
+
+def test_integrator(lib):
+    """`integrator`, test/integrator.rs:10-67: D = 3, 4^3, beta = 8; Metropolis sweeps, then symplectic steps and
+    mixed leap/sync sequences conserve H."""
+    rng = lq.Rng.seed_from_u64(SEED_RNG)
+    state = lq.LatticeStateDefault.new_determinist(1000.0, 8.0, 4, rng, D=3, lib=lib)
+    mh = lq.MetropolisHastingsSweep.new(1, 0.1, rng)
+    for _ in range(10):
+        state = state.monte_carlo_step(mh)
+    assert 0.0 < mh.prob_replace_mean() <= 1.0 and 0 <= mh.number_replace_last() <= 3 * 64
+    state.normalize_link_matrices()
+    integ = lq.SymplecticEulerCuda()
+    st = lq.LatticeStateEFSyncDefault.new_random_e_state(state, rng)
+    h = st.hamiltonian_total()
+    st2 = st.simulate_symplectic_n_auto(integ, 1e-4, 10)
+    assert abs(h - st2.hamiltonian_total()) < 1e-4
+    st3 = st.simulate_to_leapfrog(integ, 1e-4).simulate_leap_n(integ, 1e-4, 2).simulate_to_synchronous(integ, 1e-4)
+    assert abs(h - st3.hamiltonian_total()) < 1e-5
+    st4 = st.simulate_symplectic(integ, 1e-4)
+    st5 = st.simulate_symplectic_n(integ, 1e-4, 1)
+    assert np.array_equal(st4.link_matrix(), st5.link_matrix()) and np.array_equal(st4.e_field(), st5.e_field())
+
+
+def test_hmc_like_the_doc_example(lib):
+    """hybrid_monte_carlo.rs doc example (:23-52) + config 1 of BASELINE.json (8^4 shrunk to 4^4 on the CPU CI):
+    HybridMonteCarloDiagnostic + symplectic Euler, trajectories compared with the oracle from the same start
+    configuration and the same Philox momenta."""
+    n = 4
+    rng = lq.Rng.seed_from_u64(SEED_RNG)
+    state = lq.LatticeStateDefault.new_determinist(1.0, 6.0, n, rng, lib=lib)
+    o = Oracle(4, n, a=1.0, beta=6.0)
+    U = np.array(state.link_matrix())
+    hmc = lq.HybridMonteCarloDiagnostic.new(0.01, 10, lq.SymplecticEulerCuda.new(), rng)
+    probe = lq.Rng(rng.state)  # replays the (seed, counter) pairs the method will draw
+    for _ in range(3):
+        seed, counter = probe.next_u64(), probe.next_u64() >> 8
+        state = state.monte_carlo_step(hmc)
+        ro = o.hmc_trajectory(U, 0.01, 10, seed, counter)
+        assert hmc.has_replace_last() == ro["accepted"]
+        assert abs(hmc.prob_replace_last() - ro["prob"]) <= 1e-6
+        assert hmc.gauss_steps_last == ro["gauss_steps"]
+        U = ro["U"]
+        assert np.abs(state.link_matrix() - U).max() <= 1e-10
+    p = state.average_trace_plaquette().real / 3.0
+    assert abs(p - o.average_trace_plaquette(U).real / 3.0) <= 1e-12
+    assert isinstance(state, lq.LatticeStateDefault)  # next_element returns the plain link state (state_owned)
+
+
+def test_sweeps_through_monte_carlo_trait(lib):
+    """heat_bath.rs / overrelaxation.rs doc examples: state.monte_carlo_step(&mut method) in a loop;
+    over-relaxation conserves the action (same_energy_rotation/reverse, overrelaxation.rs:220-253)."""
+    rng = lq.Rng.seed_from_u64(SEED_RNG)
+    state = lq.LatticeStateDefault.new_determinist(1.0, 2.0, 4, rng, lib=lib)
+    hb = lq.HeatBathSweep.new(rng)
+    p0 = state.average_trace_plaquette().real / 3.0
+    for _ in range(5):
+        state = state.monte_carlo_step(hb)
+    p1 = state.average_trace_plaquette().real / 3.0
+    assert p1 > p0 + 0.1  # a hot start orders under the heat bath
+    for method in (lq.OverrelaxationSweepReverse.new(), lq.OverrelaxationSweepRotation.new()):
+        h = state.hamiltonian_links()
+        state = state.monte_carlo_step(method)
+        assert abs(h - state.hamiltonian_links()) <= 1e-10 * abs(h)
+    combo = lq.HybridMethodVec([hb, lq.OverrelaxationSweepReverse.new()])
+    state = state.monte_carlo_step(combo)
+    state.normalize_link_matrices()
+    assert np.isfinite(state.hamiltonian_links())
