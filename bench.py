@@ -173,7 +173,9 @@ def run_ours(args):
         dc = DistContext(4, gext, a=SPACING, beta=BETA, proc_grid=pg)
         ctx = dc.ctx
         stream = torch.cuda.current_stream(dev)
-        par = "x".join(str(p) for p in pg) + " ranks (z,t split), one-site halos over NCCL"
+        par = ("x".join(str(p) for p in pg) + " ranks (z,t split), one-site halos: " +
+               ("boundary slices stored into the neighbours' ghost layers over NVLink by our own kernels (CUDA IPC "
+                "peer memory, release/acquire flags)" if dc.transport == "p2p" else "NCCL send/recv through callbacks"))
     else:
         from lattice_qcd_rs_b200 import Context
         ctx = Context(4, L, a=SPACING, beta=BETA, device=local)

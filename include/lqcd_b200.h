@@ -48,8 +48,12 @@ enum { LQ_OR_ROTATION = 0, LQ_OR_REVERSE = 1 };
 /* behaviour flags (lq_set_flags) */
 enum {
   LQ_FLAG_PAULI3_FIXED = 1,   /* use sigma_3 = diag(1,-1); default restates su2.rs:39-45 as coded (diag(1,1)) */
-  LQ_FLAG_NO_KICK_MERGE = 2   /* lq_symplectic_n: do not merge the two adjacent dt/2 E-kicks of consecutive steps
+  LQ_FLAG_NO_KICK_MERGE = 2,  /* lq_symplectic_n: do not merge the two adjacent dt/2 E-kicks of consecutive steps
                                  (results are bit-identical either way; this only changes the launch count)    */
+  LQ_FLAG_GAUSS_FUSED = 4     /* lq_gauss_project(_step): one fused kernel per iteration (projection step + Gauss
+                                 field of the projected E, backward neighbours recomputed: 1376 instead of 2208
+                                 B/site but 32 instead of 20 matrix products/site) instead of two passes.  Same
+                                 results; measured slower on B200 (0.49 vs 0.43 ms at 32^4), so off by default */
 };
 
 const char* lq_strerror(int code);
@@ -166,6 +170,18 @@ int lq_halo_bytes(lq_ctx*, int which, int dir, int64_t* bytes);
 int lq_halo_pack(lq_ctx*, int which, int dir, int side, void* d_buf, int64_t bytes);
 int lq_halo_unpack(lq_ctx*, int which, int dir, int side, const void* d_buf, int64_t bytes);
 int lq_halo_invalidate(lq_ctx*, int which);
+/* Peer-to-peer transport (preferred on one NVLink node): each rank exports CUDA-IPC handles of its field buffers
+ * (7 x 64 bytes: U U2 E E2 G G2 flags), the caller all-gathers them and attaches the neighbours' handles; from then
+ * on every ghost refresh is done by the library's own kernels writing the boundary slices straight into the
+ * neighbours' ghost layers over NVLink, ordered by release/acquire flags in peer memory (no pack buffers, no NCCL,
+ * no host round trip).  `offsets` = n_neighbors x D entries in {-1,0,+1}: the list must be identical on every rank
+ * and closed under negation; peer_index[k] selects which of the n_peers opened handle sets neighbour k lives in
+ * (two neighbours may be the same rank).  allreduce_sum of lq_set_comm is still used for the global sums. */
+int lq_p2p_export(lq_ctx*, void* handles_out, int64_t bytes /* 7 * 64 */);
+int lq_p2p_attach(lq_ctx*, int n_peers, const void* peer_handles, int n_neighbors, const int* offsets,
+                  const int* peer_index);
+int lq_p2p_enabled(const lq_ctx*);
+int64_t lq_p2p_exchanges(const lq_ctx*);
 
 /* ---- measurement ---------------------------------------------------------------------------------------------
  * Optional CUDA-event timing of kernel classes on the context stream (used by bench.py for the roofline line:

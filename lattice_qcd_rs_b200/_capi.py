@@ -24,7 +24,7 @@ ERRORS = {
 }
 SYNC_SYNC, LEAP_LEAP, SYNC_LEAP, LEAP_SYNC, SYMPLECTIC = range(5)
 OR_ROTATION, OR_REVERSE = 0, 1
-FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE = 1, 2
+FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED = 1, 2, 4
 
 HALO_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, C.c_int)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _vp, _dp, C.c_int)
@@ -105,6 +105,10 @@ SYMBOLS = {
     "lq_halo_pack": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int64]),
     "lq_halo_unpack": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int64]),
     "lq_halo_invalidate": (C.c_int, [_vp, C.c_int]),
+    "lq_p2p_export": (C.c_int, [_vp, _vp, C.c_int64]),
+    "lq_p2p_attach": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _ip, _ip]),
+    "lq_p2p_enabled": (C.c_int, [_vp]),
+    "lq_p2p_exchanges": (C.c_int64, [_vp]),
     "lq_profile_enable": (C.c_int, [_vp, C.c_int]),
     "lq_profile_reset": (C.c_int, [_vp]),
     "lq_profile_get": (C.c_int, [_vp, C.c_int, _i64p, _dp]),
@@ -433,6 +437,28 @@ class Context:
 
     def halo_unpack(self, which, d, side, ptr, nbytes):
         self._check(self.lib.lq_halo_unpack(self._h, which, d, side, _vp(ptr), nbytes), "lq_halo_unpack")
+
+    # -- peer-to-peer transport
+    def p2p_export(self):
+        buf = C.create_string_buffer(7 * 64)
+        self._check(self.lib.lq_p2p_export(self._h, buf, 7 * 64), "lq_p2p_export")
+        return buf.raw
+
+    def p2p_attach(self, peer_handles, offsets, peer_index):
+        """peer_handles: list of 448-byte blobs (one per unique peer); offsets: list of D-vectors; peer_index: list."""
+        blob = b"".join(peer_handles)
+        n_nb = len(offsets)
+        off = (C.c_int * (n_nb * self.D))(*[int(v) for o in offsets for v in o])
+        pi = (C.c_int * n_nb)(*[int(v) for v in peer_index])
+        self._check(self.lib.lq_p2p_attach(self._h, len(peer_handles), C.c_char_p(blob), n_nb, off, pi), "lq_p2p_attach")
+
+    @property
+    def p2p_enabled(self):
+        return bool(self.lib.lq_p2p_enabled(self._h))
+
+    @property
+    def p2p_exchanges(self):
+        return int(self.lib.lq_p2p_exchanges(self._h))
 
     def halo_invalidate(self, which):
         self._check(self.lib.lq_halo_invalidate(self._h, which), "lq_halo_invalidate")

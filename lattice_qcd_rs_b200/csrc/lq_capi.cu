@@ -20,6 +20,9 @@
 
 #define LQ_BLOCK 128
 #define LQ_RBLOCK 256
+#define LQ_P2P_NBUF 7      /* U U2 E E2 G G2 flags */
+#define LQ_P2P_MAXNB 8     /* 3^2 - 1 neighbours of a 2-D process grid */
+#define LQ_P2P_HANDLE 64   /* sizeof(cudaIpcMemHandle_t) */
 #define LQ_PROF_CAP 8192
 
 static thread_local char g_cuda_err[512] = "";
@@ -100,7 +103,7 @@ struct lq_ctx {
   bool decomposed;
   int nproc[LQ_MAXD];
   bool even_extents;
-  cx *U, *U2, *E, *E2, *G;
+  cx *U, *U2, *E, *E2, *G, *G2;
   cx *snapU, *snapE;
   int64_t snap_t;
   bool has_snap;
@@ -114,6 +117,17 @@ struct lq_ctx {
   bool g_valid;  // the Gauss field in G matches the current (U, E)
   lq_comm comm;
   bool has_comm;
+  // peer-to-peer halo transport (CUDA IPC mappings of the neighbours' buffers, written over NVLink by our kernels)
+  bool p2p_on;
+  cx* own[LQ_P2P_NBUF - 1];                       // the six field allocations in export order: U U2 E E2 G G2
+  unsigned long long* p2p_flags;                  // [LQ_P2P_MAXNB] incoming flags + [LQ_P2P_MAXNB] error word
+  unsigned long long p2p_epoch;
+  int p2p_nnb, p2p_npeers;
+  int p2p_off[LQ_P2P_MAXNB][LQ_MAXD];             // neighbour offsets (-1, 0, +1 per direction)
+  int p2p_peer[LQ_P2P_MAXNB];                     // neighbour -> opened peer
+  int p2p_rev[LQ_P2P_MAXNB];                      // my slot in that neighbour's flag array
+  void* p2p_base[LQ_P2P_MAXNB][LQ_P2P_NBUF];      // opened peer buffers (per unique peer)
+  int64_t p2p_exchanges;
   // optional per-kernel-class CUDA-event timing (lq_profile_*)
   bool prof_on;
   int prof_n;                 // event pairs recorded since the last reset
@@ -287,8 +301,14 @@ static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ helpers
+static int p2p_exchange(lq_ctx* c, int which);
 static int ensure_halo(lq_ctx* c, int which) {
   if (!c->decomposed || c->halo_ok[which]) return LQ_OK;
+  if (c->p2p_on) {
+    LQ_TRY(p2p_exchange(c, which));
+    c->halo_ok[which] = true;
+    return LQ_OK;
+  }
   if (!c->has_comm || !c->comm.halo_exchange) return LQ_E_COMM;
   int rc = c->comm.halo_exchange(c->comm.user, c, which);
   if (rc) return LQ_E_COMM;
@@ -297,6 +317,14 @@ static int ensure_halo(lq_ctx* c, int which) {
 }
 static int global_sum(lq_ctx* c, double* v, int n) {
   if (!c->decomposed) return LQ_OK;
+#ifndef LQ_HOST_EMU
+  if (c->p2p_on) {  // a flag wait that timed out (a neighbour died or left the SPMD sequence) latched an error word
+    unsigned long long err = 0;
+    LQ_CHECK(cudaMemcpyAsync(&err, c->p2p_flags + LQ_P2P_MAXNB, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
+    LQ_TRY(rt_sync(c->stream));
+    if (err) return LQ_E_COMM;
+  }
+#endif
   if (!c->has_comm || !c->comm.allreduce_sum) return LQ_OK;  // rank-local partial sums
   return c->comm.allreduce_sum(c->comm.user, v, n) ? LQ_E_COMM : LQ_OK;
 }
@@ -447,6 +475,13 @@ int lq_ctx_destroy(lq_ctx* c) {
   rt_free(c->E);
   rt_free(c->E2);
   rt_free(c->G);
+  rt_free(c->G2);
+#ifndef LQ_HOST_EMU
+  for (int q = 0; q < c->p2p_npeers; ++q)
+    for (int b = 0; b < LQ_P2P_NBUF; ++b)
+      if (c->p2p_base[q][b]) cudaIpcCloseMemHandle(c->p2p_base[q][b]);
+  rt_free(c->p2p_flags);
+#endif
   rt_free(c->snapU);
   rt_free(c->snapE);
   rt_free(c->d_aos);
@@ -885,16 +920,36 @@ int lq_gauss_sum_div(lq_ctx* c, double* out) {
 int lq_gauss_project_step(lq_ctx* c) {
   if (!c) return LQ_E_BADARG;
   LQ_GUARD(c);
-  LQ_TRY(gauss_field(c));
-  LQ_TRY(ensure_halo(c, 2));
+  LQ_TRY(gauss_field(c));     // G of the current (U, E); a no-op when the previous iteration left it behind
+  LQ_TRY(ensure_halo(c, 2));  // G(x +- i)
+  LQ_TRY(ensure_halo(c, 1));  // E_i(x - i)
+  LQ_TRY(ensure_halo(c, 0));
   LQ_TRY(ensure_buf(&c->E2, c->e_bytes(), c));
-  ProfScope ps(c, LQ_PROF_GAUSS_STEP);
-  LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KGaussProjectStep<DD>{c->g, c->U, c->G, c->E, c->E2}))));
+  if (!(c->flags & LQ_FLAG_GAUSS_FUSED)) {
+    ProfScope ps(c, LQ_PROF_GAUSS_STEP);
+    LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KGaussProjectStep<DD>{c->g, c->U, c->G, c->E, c->E2}))));
+    cx* t = c->E;
+    c->E = c->E2;
+    c->E2 = t;
+    c->halo_ok[1] = false;
+    c->g_valid = false;
+    return LQ_OK;
+  }
+  LQ_TRY(ensure_buf(&c->G2, c->g_bytes(), c));
+  {
+    // projection step + Gauss field of the projected E in one pass (KGaussIter)
+    ProfScope ps(c, LQ_PROF_GAUSS_STEP);
+    LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussIter<DD>{c->g, c->U, c->G, c->E, c->E2, c->G2}))));
+  }
   cx* t = c->E;
   c->E = c->E2;
   c->E2 = t;
-  c->halo_ok[1] = false;
-  c->g_valid = false;
+  t = c->G;
+  c->G = c->G2;
+  c->G2 = t;
+  c->halo_ok[1] = true;   // the low-ghost entries consumers read were recomputed by the kernel
+  c->halo_ok[2] = false;
+  c->g_valid = true;
   return LQ_OK;
 }
 int lq_gauss_project(lq_ctx* c, int64_t max_steps, int64_t* steps_out) {
@@ -1074,6 +1129,210 @@ int lq_profile_get(lq_ctx* c, int kernel_class, int64_t* launches, double* total
 #endif
   return LQ_OK;
 }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- peer-to-peer halos
+// One process per GPU; every rank maps its neighbours' field buffers (CUDA IPC) and WRITES its boundary slices
+// straight into their ghost layers over NVLink -- no pack buffers, no NCCL, no host round trip.  An exchange is
+//   barrier(ready) -> push kernels (one per neighbour) -> barrier(data)
+// where a barrier is one tiny kernel: lane t releases a monotonically increasing epoch into its slot of neighbour
+// t's flag array (st.release.sys), then spins (ld.acquire.sys) until neighbour t's epoch arrives in mine.
+// "ready" orders the push after the neighbours' earlier kernels that still read their ghosts (WAR), "data" orders
+// the consumers after the neighbours' pushes (RAW).  All ranks issue the same sequence of exchanges (SPMD), so
+// the epochs match; a spin gives up after ~20 s and latches an error word that lq_sync / reductions report.
+#ifndef LQ_HOST_EMU
+struct P2pBarrierArgs {
+  unsigned long long* remote[LQ_P2P_MAXNB];
+  int n;
+};
+__global__ void lq_p2p_barrier_k(P2pBarrierArgs a, unsigned long long* mine, unsigned long long value) {
+  const int t = threadIdx.x;
+  if (t >= a.n) return;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.remote[t]), "l"(value) : "memory");
+  const long long t0 = clock64();
+  unsigned long long v;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + t) : "memory");
+    if (v >= value) break;
+    if (clock64() - t0 > 40000000000ll) {
+      mine[LQ_P2P_MAXNB] = value;  // error latch
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+// boundary slice -> the neighbour's ghost slice.  region: lo[d], len[d] in storage coordinates; delta = slot shift.
+template <int D>
+struct KHaloPush {
+  LqGeom g;
+  const cx* F;
+  cx* dst;
+  int planes;
+  int lo[LQ_MAXD], len[LQ_MAXD];
+  lq_i64 nsite, delta;
+  LQ_HD void operator()(lq_i64 i) const {
+    lq_i64 pl = i / nsite;
+    lq_i64 n = i - pl * nsite;
+    if (pl >= planes) return;
+    Site<D> st;
+    lq_i64 q = n / len[0];
+    int lane = (int)(n - q * len[0]);  // direction 0 is never split: the whole row, even x0 first
+    int x0 = lane < g.ne0 ? 2 * lane : 2 * (lane - g.ne0) + 1;
+    st.x[0] = x0;
+    st.s = x0;
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      lq_i64 r = q / len[d];
+      int xd = lo[d] + (int)(q - r * len[d]);
+      q = r;
+      st.x[d] = xd;
+      st.s += (lq_i64)xd * g.sstride[d];
+    }
+    lq_i64 p = lq_slot<D>(g, st);
+    dst[lq_addr(p + delta, planes, (int)pl)] = F[lq_addr(p, planes, (int)pl)];
+  }
+};
+static int p2p_barrier(lq_ctx* c) {
+  P2pBarrierArgs a;
+  a.n = c->p2p_nnb;
+  for (int k = 0; k < c->p2p_nnb; ++k)
+    a.remote[k] = (unsigned long long*)c->p2p_base[c->p2p_peer[k]][LQ_P2P_NBUF - 1] + c->p2p_rev[k];
+  c->p2p_epoch += 1;
+  lq_p2p_barrier_k<<<1, 32, 0, c->stream>>>(a, c->p2p_flags, c->p2p_epoch);
+  c->launches++;
+  LQ_CHECK(cudaGetLastError());
+  return LQ_OK;
+}
+static int p2p_exchange(lq_ctx* c, int which) {
+  cx* f;
+  int planes;
+  switch (which) {
+    case 0: f = c->U; planes = 9 * c->g.D; break;
+    case 1: f = c->E; planes = 4 * c->g.D; break;
+    case 2: f = c->G; planes = 9; break;
+    default: return LQ_E_BADARG;
+  }
+  if (!f) return LQ_E_BADARG;
+  int bi = -1;  // which of my allocations is it: the neighbours' current buffer is their allocation of the same index
+  for (int b = 0; b < LQ_P2P_NBUF - 1; ++b)
+    if (c->own[b] == f) bi = b;
+  if (bi < 0) return LQ_E_COMM;
+  LQ_TRY(p2p_barrier(c));  // ready: the neighbours' earlier kernels are done with their ghosts
+  const LqGeom& g = c->g;
+  for (int k = 0; k < c->p2p_nnb; ++k) {
+    int lo[LQ_MAXD], len[LQ_MAXD];
+    lq_i64 ns = 1, delta = 0;
+    for (int d = 0; d < LQ_MAXD; ++d) {
+      int o = d < g.D ? c->p2p_off[k][d] : 0;
+      if (d >= g.D) {
+        lo[d] = 0;
+        len[d] = 1;
+      } else if (o < 0) {  // my first interior slice -> their high ghost
+        lo[d] = 1;
+        len[d] = 1;
+        delta += (lq_i64)g.ext[d] * g.sstride[d];
+      } else if (o > 0) {  // my last interior slice -> their low ghost
+        lo[d] = g.ext[d];
+        len[d] = 1;
+        delta -= (lq_i64)g.ext[d] * g.sstride[d];
+      } else {
+        lo[d] = g.ghost[d];
+        len[d] = g.ext[d];
+      }
+      ns *= len[d];
+    }
+    cx* dst = (cx*)c->p2p_base[c->p2p_peer[k]][bi];
+#define LQ_PUSH(DD_)                                                                                   \
+  {                                                                                                    \
+    KHaloPush<DD_> kp;                                                                                 \
+    kp.g = g; kp.F = f; kp.dst = dst; kp.planes = planes; kp.nsite = ns; kp.delta = delta;            \
+    for (int d = 0; d < LQ_MAXD; ++d) { kp.lo[d] = lo[d]; kp.len[d] = len[d]; }                       \
+    LQ_TRY(launch(c, ns * planes, kp));                                                                \
+  }
+    switch (g.D) {
+      case 2: LQ_PUSH(2) break;
+      case 3: LQ_PUSH(3) break;
+      case 4: LQ_PUSH(4) break;
+      default: return LQ_E_BADARG;
+    }
+#undef LQ_PUSH
+  }
+  LQ_TRY(p2p_barrier(c));  // data: the neighbours' pushes into my ghosts have landed
+  c->p2p_exchanges++;
+  return LQ_OK;
+}
+#else
+static int p2p_exchange(lq_ctx*, int) { return LQ_E_COMM; }
+#endif
+
+extern "C" {
+int lq_p2p_export(lq_ctx* c, void* handles_out, int64_t bytes) {
+  if (!c || !handles_out || bytes != LQ_P2P_NBUF * LQ_P2P_HANDLE) return LQ_E_BADARG;
+#ifdef LQ_HOST_EMU
+  return LQ_E_NODEVICE;
+#else
+  if (!c->decomposed) return LQ_E_BADARG;
+  LQ_GUARD(c);
+  // every buffer a neighbour may have to write must exist before the handles travel
+  LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
+  LQ_TRY(ensure_buf(&c->E2, c->e_bytes(), c));
+  LQ_TRY(ensure_buf(&c->G, c->g_bytes(), c));
+  LQ_TRY(ensure_buf(&c->G2, c->g_bytes(), c));
+  if (!c->p2p_flags) {
+    LQ_TRY(rt_malloc((void**)&c->p2p_flags, 2 * LQ_P2P_MAXNB * sizeof(unsigned long long)));
+    LQ_TRY(rt_memset(c->p2p_flags, 0, 2 * LQ_P2P_MAXNB * sizeof(unsigned long long), c->stream));
+  }
+  LQ_TRY(rt_sync(c->stream));
+  cx* bufs[LQ_P2P_NBUF - 1] = {c->U, c->U2, c->E, c->E2, c->G, c->G2};
+  for (int b = 0; b < LQ_P2P_NBUF - 1; ++b) c->own[b] = bufs[b];
+  static_assert(sizeof(cudaIpcMemHandle_t) == LQ_P2P_HANDLE, "IPC handle size");
+  cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles_out;
+  for (int b = 0; b < LQ_P2P_NBUF - 1; ++b) LQ_CHECK(cudaIpcGetMemHandle(&h[b], bufs[b]));
+  LQ_CHECK(cudaIpcGetMemHandle(&h[LQ_P2P_NBUF - 1], c->p2p_flags));
+  return LQ_OK;
+#endif
+}
+int lq_p2p_attach(lq_ctx* c, int n_peers, const void* peer_handles, int n_neighbors, const int* offsets,
+                  const int* peer_index) {
+  if (!c || !peer_handles || !offsets || !peer_index) return LQ_E_BADARG;
+#ifdef LQ_HOST_EMU
+  return LQ_E_NODEVICE;
+#else
+  if (!c->decomposed || !c->p2p_flags || n_peers < 1 || n_peers > LQ_P2P_MAXNB || n_neighbors < 1 ||
+      n_neighbors > LQ_P2P_MAXNB)
+    return LQ_E_BADARG;
+  LQ_GUARD(c);
+  const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)peer_handles;
+  for (int q = 0; q < n_peers; ++q)
+    for (int b = 0; b < LQ_P2P_NBUF; ++b)
+      LQ_CHECK(cudaIpcOpenMemHandle(&c->p2p_base[q][b], h[q * LQ_P2P_NBUF + b], cudaIpcMemLazyEnablePeerAccess));
+  c->p2p_npeers = n_peers;
+  // neighbour slots are numbered by their offset vector, identically on every rank: slot(o) = sum (o_d + 1) 3^d
+  // over the directions; a neighbour at offset o finds me at offset -o.
+  for (int k = 0; k < n_neighbors; ++k) {
+    if (peer_index[k] < 0 || peer_index[k] >= n_peers) return LQ_E_BADARG;
+    c->p2p_peer[k] = peer_index[k];
+    for (int d = 0; d < LQ_MAXD; ++d) c->p2p_off[k][d] = d < c->g.D ? offsets[k * c->g.D + d] : 0;
+  }
+  for (int k = 0; k < n_neighbors; ++k) {
+    int rev = -1;
+    for (int j = 0; j < n_neighbors; ++j) {
+      bool opp = true;
+      for (int d = 0; d < c->g.D; ++d) opp = opp && c->p2p_off[j][d] == -c->p2p_off[k][d];
+      if (opp) rev = j;
+    }
+    if (rev < 0) return LQ_E_BADARG;  // the neighbour list must be closed under negation, in the same order everywhere
+    c->p2p_rev[k] = rev;
+  }
+  c->p2p_nnb = n_neighbors;
+  c->p2p_epoch = 0;
+  c->p2p_on = true;
+  return LQ_OK;
+#endif
+}
+int lq_p2p_enabled(const lq_ctx* c) { return c && c->p2p_on ? 1 : 0; }
+int64_t lq_p2p_exchanges(const lq_ctx* c) { return c ? c->p2p_exchanges : 0; }
 
 // ---------------------------------------------------------------------------------------------- halos
 static int halo_field(lq_ctx* c, int which, cx** f, int* planes) {

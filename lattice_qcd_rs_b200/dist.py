@@ -8,6 +8,10 @@ every kernel itself and asks this module for exactly two services through `lq_se
   * allreduce_sum(vals): global sums of a few f64 (plaquette, Hamiltonians, Gauss residual, accept statistics).
 Nothing here computes on the lattice; torch is device memory + transport only.
 """
+import itertools
+import os
+import sys
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -61,8 +65,55 @@ class DistContext:
         self._scratch = torch.zeros(16, dtype=torch.float64, device=self.device)
         self.halo_exchanges = 0
         self.halo_bytes_sent = 0
+        self.transport = "none"
         if self.world > 1:
             self.ctx.set_comm(self._halo_exchange, self._allreduce_sum)
+            self.transport = "nccl-callbacks"
+            if self.on_cuda and os.environ.get("LQ_HALO_TRANSPORT", "p2p") == "p2p":
+                self._setup_p2p()
+
+    # ------------------------------------------------------------------ peer-to-peer transport (CUDA IPC over NVLink)
+    def neighbour_offsets(self):
+        """All offsets in {-1,0,1} over the split directions except 0, in an order every rank agrees on."""
+        dec = [d for d in range(self.D) if self.proc_grid[d] > 1]
+        out = []
+        for combo in itertools.product((-1, 0, 1), repeat=len(dec)):
+            if any(combo):
+                o = [0] * self.D
+                for d, v in zip(dec, combo):
+                    o[d] = v
+                out.append(o)
+        return out
+
+    def _setup_p2p(self):
+        """Exchange IPC handles of the field buffers once; afterwards ghost refreshes are the library's own kernels
+        storing into the neighbours' memory.  Falls back to the NCCL callbacks when IPC/peer access is unavailable
+        (every rank takes the same decision)."""
+        ok, mine = 1, b""
+        try:
+            mine = self.ctx.p2p_export()
+        except Exception as e:  # noqa: BLE001
+            print(f"[lattice_qcd_rs_b200] rank {self.rank}: p2p export failed ({e}); using NCCL halos", file=sys.stderr)
+            ok = 0
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (ok, mine), group=self.group)
+        if not all(g[0] for g in gathered):
+            return
+        offs = self.neighbour_offsets()
+        ranks = [self._rank_of([c + o for c, o in zip(self.coord, off)]) for off in offs]
+        peers = sorted(set(ranks))
+        try:
+            self.ctx.p2p_attach([gathered[r][1] for r in peers], offs, [peers.index(r) for r in ranks])
+            ok = 1
+        except Exception as e:  # noqa: BLE001
+            print(f"[lattice_qcd_rs_b200] rank {self.rank}: p2p attach failed ({e}); using NCCL halos", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self.transport = "p2p"
+        else:
+            raise RuntimeError("peer-to-peer attach succeeded on some ranks only; set LQ_HALO_TRANSPORT=nccl")
 
     # ------------------------------------------------------------------ rank geometry
     def _rank_of(self, coord):

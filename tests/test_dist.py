@@ -26,13 +26,14 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, backend, D, gext, proc_grid, q):
+def _worker(rank, world, port, backend, D, gext, proc_grid, q, transport="p2p"):
     try:
         if ROOT not in sys.path:
             sys.path.insert(0, ROOT)
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
         os.environ.setdefault("OMP_NUM_THREADS", "2")
+        os.environ["LQ_HALO_TRANSPORT"] = transport
         if backend == "nccl":
             torch.cuda.set_device(rank)
         dist.init_process_group(backend, rank=rank, world_size=world)
@@ -94,7 +95,8 @@ def _worker(rank, world, port, backend, D, gext, proc_grid, q):
         na, sp = c.sweep_metropolis(SEED, 13, spread=0.1, n_update=2)
         Uo, nao, spo = o.sweep_metropolis(U, SEED, 13, n_update=2, spread=0.1)
         res["metropolis"] = rel(dc.gather(c.links_download(), 18), Uo) + abs(na - nao) + abs(sp - spo) / spo
-        res["exchanges"] = dc.halo_exchanges
+        res["exchanges"] = dc.halo_exchanges + c.p2p_exchanges
+        res["transport"] = dc.transport
         if rank == 0:
             q.put(res)
         dist.barrier()
@@ -107,11 +109,12 @@ def _worker(rank, world, port, backend, D, gext, proc_grid, q):
         raise
 
 
-def _run(world, backend, D, gext, proc_grid):
+def _run(world, backend, D, gext, proc_grid, transport="p2p"):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, D, gext, proc_grid, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, D, gext, proc_grid, q, transport))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = q.get(timeout=600)
@@ -127,7 +130,7 @@ TOL = {"roundtrip": 0.0, "hmc_acc": 0.0}
 def _check(res):
     assert res["exchanges"] > 0
     for k, v in res.items():
-        if k == "exchanges":
+        if k in ("exchanges", "transport"):
             continue
         tol = TOL.get(k, 1e-9 if k in ("heatbath", "overrelax", "metropolis", "hmc_U") else 1e-12)
         assert v <= tol, (k, v, res)
@@ -147,6 +150,11 @@ def test_decomposed_matches_oracle_nccl():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
-    _check(_run(2, "nccl", 4, [8, 8, 8, 16], [1, 1, 1, 2]))
-    if n >= 4:
-        _check(_run(4, "nccl", 4, [8, 8, 8, 8], [1, 1, 2, 2]))
+    for transport in ("p2p", "nccl"):  # peer-memory pushes by our own kernels / NCCL send-recv through the callbacks
+        res = _run(2, "nccl", 4, [8, 8, 8, 16], [1, 1, 1, 2], transport)
+        _check(res)
+        assert res["transport"] == ("p2p" if transport == "p2p" else "nccl-callbacks"), res["transport"]
+        if n >= 4:
+            res = _run(4, "nccl", 4, [8, 8, 8, 8], [1, 1, 2, 2], transport)
+            _check(res)
+            assert res["transport"] == ("p2p" if transport == "p2p" else "nccl-callbacks"), res["transport"]

@@ -230,9 +230,17 @@ def test_gauss(backend, D, ext):
     c.efield_upload(E)
     assert rel(c.gauss_field(), o.gauss_field(U, E)) <= RTOL
     assert abs(c.gauss_sum_div() - o.gauss_sum_div(U, E)) <= RTOL * o.gauss_sum_div(U, E)
-    c.gauss_project_step()
     E1 = o.project_to_gauss_step(U, E)
-    assert rel(c.efield_download(), E1) <= RTOL
+    for flags in (0, 4):  # two passes (default) and LQ_FLAG_GAUSS_FUSED (one fused kernel per iteration): same results
+        c.set_flags(flags)
+        c.efield_upload(E)
+        c.gauss_project_step()
+        assert rel(c.efield_download(), E1) <= RTOL
+        # the Gauss field the fused kernel left behind is the Gauss field of the projected E
+        assert rel(c.gauss_field(), o.gauss_field(U, E1)) <= RTOL
+        c.gauss_project_step()
+        assert rel(c.efield_download(), o.project_to_gauss_step(U, E1)) <= RTOL
+    c.set_flags(0)
     c.efield_upload(E)
     it = c.gauss_project()
     Eo, ito = o.project_to_gauss(U, E)
