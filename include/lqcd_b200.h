@@ -50,6 +50,8 @@ enum {
   LQ_FLAG_PAULI3_FIXED = 1,   /* use sigma_3 = diag(1,-1); default restates su2.rs:39-45 as coded (diag(1,1)) */
   LQ_FLAG_NO_KICK_MERGE = 2,  /* lq_symplectic_n: do not merge the two adjacent dt/2 E-kicks of consecutive steps
                                  (results are bit-identical either way; this only changes the launch count)    */
+  LQ_FLAG_GENERIC_KERNELS = 8, /* use the dimension-generic functor kernels even where a tuned D = 4 kernel exists
+                                 (the parity tests run both; results agree to rounding of the staple order)   */
   LQ_FLAG_GAUSS_FUSED = 4     /* lq_gauss_project(_step): one fused kernel per iteration (projection step + Gauss
                                  field of the projected E, backward neighbours recomputed: 1376 instead of 2208
                                  B/site but 32 instead of 20 matrix products/site) instead of two passes.  Same

@@ -24,7 +24,7 @@ ERRORS = {
 }
 SYNC_SYNC, LEAP_LEAP, SYNC_LEAP, LEAP_SYNC, SYMPLECTIC = range(5)
 OR_ROTATION, OR_REVERSE = 0, 1
-FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED = 1, 2, 4
+FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED, FLAG_GENERIC_KERNELS = 1, 2, 4, 8
 
 HALO_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, C.c_int)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _vp, _dp, C.c_int)

@@ -128,6 +128,7 @@ struct lq_ctx {
   int p2p_rev[LQ_P2P_MAXNB];                      // my slot in that neighbour's flag array
   void* p2p_base[LQ_P2P_MAXNB][LQ_P2P_NBUF];      // opened peer buffers (per unique peer)
   int64_t p2p_exchanges;
+  void* d_push;                                   // LqPush[6] on the device: peer table per link-buffer allocation
   // optional per-kernel-class CUDA-event timing (lq_profile_*)
   bool prof_on;
   int prof_n;                 // event pairs recorded since the last reset
@@ -302,6 +303,9 @@ static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
 
 // ------------------------------------------------------------------------------------------------ helpers
 static int p2p_exchange(lq_ctx* c, int which);
+#ifndef LQ_HOST_EMU
+static int p2p_barrier(lq_ctx* c);
+#endif
 static int ensure_halo(lq_ctx* c, int which) {
   if (!c->decomposed || c->halo_ok[which]) return LQ_OK;
   if (c->p2p_on) {
@@ -481,6 +485,7 @@ int lq_ctx_destroy(lq_ctx* c) {
     for (int b = 0; b < LQ_P2P_NBUF; ++b)
       if (c->p2p_base[q][b]) cudaIpcCloseMemHandle(c->p2p_base[q][b]);
   rt_free(c->p2p_flags);
+  rt_free(c->d_push);
 #endif
   rt_free(c->snapU);
   rt_free(c->snapE);
@@ -749,7 +754,7 @@ static int efield_step(lq_ctx* c, double dt, int nkick) {
   LQ_TRY(ensure_halo(c, 0));
   ProfScope ps(c, LQ_PROF_EFIELD_STEP);
 #ifdef LQ_TUNED
-  if (lq_tuned_ok(c->g)) {
+  if (lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
     LQ_CHECK(lq_tuned_efield_step(c->stream, c->g, c->U, c->E, force_coef(c), dt, nkick));
     c->launches++;
     c->halo_ok[1] = false;
@@ -773,15 +778,40 @@ static int link_step(lq_ctx* c, const cx* Uin, cx* Uout, double dt, int use_exp)
 static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u) {
   LQ_TRY(ensure_halo(c, 0));
   LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
-  ProfScope ps(c, LQ_PROF_EFIELD_LINK_STEP);
 #ifdef LQ_TUNED
-  if (lq_tuned_ok(c->g)) {
+  const bool tuned = lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS);
+  if (tuned && c->p2p_on && c->d_push) {
+    // compute + halo push in one kernel: boundary links go straight into the neighbours' ghost layers (NVLink)
+    int bi = -1;
+    for (int b = 0; b < LQ_P2P_NBUF - 1; ++b)
+      if (c->own[b] == c->U2) bi = b;
+    if (bi < 0 || !c->d_push) return LQ_E_COMM;
+    LQ_TRY(p2p_barrier(c));  // ready: the neighbours are done reading the ghost layers this kernel overwrites
+    {
+      ProfScope ps2(c, LQ_PROF_EFIELD_LINK_STEP);
+      LQ_CHECK(lq_tuned_efield_link_step_push(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u,
+                                              link_coef(c), nkick, (const LqPush*)c->d_push + bi));
+      c->launches++;
+    }
+    LQ_TRY(p2p_barrier(c));  // data: their pushes into my ghost layers have landed
+    c->p2p_exchanges++;
+    cx* t = c->U;
+    c->U = c->U2;
+    c->U2 = t;
+    c->halo_ok[0] = true;
+    c->halo_ok[1] = false;
+    c->g_valid = false;
+    return LQ_OK;
+  }
+  if (tuned) {
+    ProfScope ps(c, LQ_PROF_EFIELD_LINK_STEP);
     LQ_CHECK(lq_tuned_efield_link_step(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u, link_coef(c),
                                        nkick));
     c->launches++;
   } else
 #endif
   {
+    ProfScope ps(c, LQ_PROF_EFIELD_LINK_STEP);
     LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g),
                                    KEfieldLinkStep<DD>{c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u, link_coef(c),
                                                        nkick, 0}))));
@@ -928,10 +958,14 @@ int lq_gauss_project_step(lq_ctx* c) {
   if (!(c->flags & LQ_FLAG_GAUSS_FUSED)) {
     ProfScope ps(c, LQ_PROF_GAUSS_STEP);
     LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KGaussProjectStep<DD>{c->g, c->U, c->G, c->E, c->E2}))));
+    for (int hd = 1; hd < c->g.D; ++hd)  // low-ghost links of the split directions: recomputed, not exchanged
+      if (c->g.ghost[hd])
+        LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / c->g.ext[hd],
+                                       KGaussProjectGhost<DD>{c->g, c->U, c->G, c->E, c->E2, hd}))));
     cx* t = c->E;
     c->E = c->E2;
     c->E2 = t;
-    c->halo_ok[1] = false;
+    c->halo_ok[1] = true;  // ensure_halo(c, 1) above made the inputs valid; the entries consumers read were updated
     c->g_valid = false;
     return LQ_OK;
   }
@@ -989,6 +1023,12 @@ int lq_sweep_heatbath(lq_ctx* c, uint64_t seed, uint64_t counter, double couplin
     for (int p = 0; p < 2; ++p) {
       LQ_TRY(ensure_halo(c, 0));
       ProfScope ps(c, LQ_PROF_HEATBATH);
+#ifdef LQ_TUNED
+      if (lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+        LQ_CHECK(lq_tuned_sweep(c->stream, c->g, c->U, 0, d, p, c->flags, 0, c->beta * coupling_scale, seed, counter));
+        c->launches++;
+      } else
+#endif
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2,
                                      KHeatBath<DD>{c->g, c->U, d, p, c->flags, c->beta * coupling_scale, seed, counter}))));
       c->halo_ok[0] = false;
@@ -1004,6 +1044,12 @@ int lq_sweep_overrelax(lq_ctx* c, int kind) {
     for (int p = 0; p < 2; ++p) {
       LQ_TRY(ensure_halo(c, 0));
       ProfScope ps(c, LQ_PROF_OVERRELAX);
+#ifdef LQ_TUNED
+      if (lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+        LQ_CHECK(lq_tuned_sweep(c->stream, c->g, c->U, 1, d, p, c->flags, kind, 0.0, 0, 0));
+        c->launches++;
+      } else
+#endif
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2, KOverrelax<DD>{c->g, c->U, d, p, kind}))));
       c->halo_ok[0] = false;
   c->g_valid = false;
@@ -1327,6 +1373,25 @@ int lq_p2p_attach(lq_ctx* c, int n_peers, const void* peer_handles, int n_neighb
   }
   c->p2p_nnb = n_neighbors;
   c->p2p_epoch = 0;
+#ifdef LQ_TUNED
+  if (c->g.D == 4) {  // peer tables of the fused "compute + halo push" MD kernel, one per buffer allocation
+    LqPush tab[LQ_P2P_NBUF - 1];
+    memset(tab, 0, sizeof(tab));
+    for (int b = 0; b < LQ_P2P_NBUF - 1; ++b) {
+      for (int i = 0; i < 9; ++i) (&tab[b].nbmap[0][0])[i] = -1;
+      for (int k = 0; k < n_neighbors; ++k) {
+        lq_i64 delta = 0;
+        for (int d = 0; d < c->g.D; ++d) delta -= (lq_i64)c->p2p_off[k][d] * c->g.ext[d] * c->g.sstride[d];
+        tab[b].peer[k] = (cx*)c->p2p_base[c->p2p_peer[k]][b];
+        tab[b].delta[k] = (int)delta;
+        tab[b].nbmap[c->p2p_off[k][2] + 1][c->p2p_off[k][3] + 1] = k;
+      }
+    }
+    if (!c->d_push) LQ_TRY(rt_malloc(&c->d_push, sizeof(tab)));
+    LQ_TRY(rt_copy(c->d_push, tab, sizeof(tab), H2D, c->stream));
+    LQ_TRY(rt_sync(c->stream));
+  }
+#endif
   c->p2p_on = true;
   return LQ_OK;
 #endif

@@ -493,6 +493,41 @@ struct KGaussProjectStep {
     lq_store_e(Eout, g, dir, p, e);
   }
 };
+// The same projection step for the links (y, hd) of the LOW ghost layer of a decomposed direction hd (the only E
+// entries of a ghost layer any kernel reads: EField::gauss needs E_i(x - i)).  Recomputing them here -- same
+// arithmetic and inputs as the rank that owns them -- keeps them valid without an E-field exchange per iteration.
+template <int D>
+struct KGaussProjectGhost {
+  LqGeom g;
+  const cx* U;
+  const cx* G;
+  const cx* Ein;
+  cx* Eout;
+  int hd;
+  LQ_HD void operator()(lq_i64 n) const {
+    Site<D> y;
+    lq_i64 q = n / g.ext[0];
+    int lane = (int)(n - q * g.ext[0]);
+    y.x[0] = lane < g.ne0 ? 2 * lane : 2 * (lane - g.ne0) + 1;
+    y.s = y.x[0];
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      int xd = 0;
+      if (d != hd) {
+        lq_i64 r = q / g.ext[d];
+        xd = (int)(q - r * g.ext[d]) + g.ghost[d];
+        q = r;
+      }
+      y.x[d] = xd;
+      y.s += (lq_i64)xd * g.sstride[d];
+    }
+    lq_i64 p = lq_slot<D>(g, y);
+    lq_i64 pp = lq_slot<D>(g, lq_up<D>(g, y, hd));
+    M3 u = lq_load_link(U, g, hd, p);
+    M3 gy = lq_load_g(G, p), gp = lq_load_g(G, pp);
+    lq_store_e(Eout, g, hd, p, lq_gauss_project_link(u, gy, gp, lq_load_e(Ein, g, hd, p)));
+  }
+};
 // One whole iteration of project_to_gauss (field.rs:1265-1294) in ONE pass: the projection step of every link of
 // site x, and the Gauss field of the projected E at x,
 //   G'(x) = sum_i [ E'_i(x) - U_i^+(x-i) E'_i(x-i) U_i(x-i) ]            (field.rs:1174-1195)

@@ -174,15 +174,46 @@ __device__ __forceinline__ M3 lq_ld36(const cx* __restrict__ U, int slot, int di
   for (int k = 0; k < 9; ++k) r.e[k] = __ldg(b + k * 32);
   return r;
 }
+// Peer table of the fused "compute + halo push" variant (PUSH = 1, decomposed contexts with the peer-to-peer
+// transport): threads that own a link of a boundary slice also store the new link straight into the ghost layer of
+// the neighbour rank(s) over NVLink.  The stores are posted, so the transfer overlaps the arithmetic of the other
+// blocks; with `bps` set the two boundary t-slices are walked first and the interior hides the whole transfer.
+struct LqPush {
+  cx* peer[8];            // neighbour k's link buffer (the allocation our Unew corresponds to)
+  int delta[8];           // slot shift into its ghost layer
+  int nbmap[3][3];        // [o_z + 1][o_t + 1] -> neighbour index or -1 (o = offset of the neighbour in directions 2, 3)
+};
 // FLAGS: 1 = visit nu so that direction 3 (first touched from DRAM by most blocks) comes last, 2 = streaming
 // (evict-first) accesses for E and U', 4 = FAKE neighbours (perfect-locality bound, kbench only: wrong results)
-template <int BLOCK, int MINB, int FUSED, int FLAGS = 0>
+template <int BLOCK, int MINB, int FUSED, int FLAGS = 0, int PUSH = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
     lq_md4_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef, double dt_e,
-                  double dt_u, double c_u, int nkick) {
+                  double dt_u, double c_u, int nkick, const LqPush* __restrict__ ps, int bps) {
+  // ps: device-resident peer table, read by the threads of boundary slices only; bps: blocks per t-slice (0: keep
+  // the natural block order)
   constexpr int SITES = BLOCK / 4;
   const int mu = threadIdx.x / SITES;
-  const int n = blockIdx.x * SITES + (threadIdx.x - mu * SITES);
+  int blk = blockIdx.x;
+  if (PUSH && bps) {
+    // The blocks of the two boundary t-slices are interleaved 1 : (S-1) with interior blocks over the first part of
+    // the grid: their NVLink stores are spread over S times their own compute time instead of saturating the link
+    // in one burst, and everything has landed long before the kernel ends.  (ext3 < 2S: first, last, interior.)
+    constexpr int S = 4;
+    const int nbb = 2 * bps;
+    if (g.ext[3] >= 2 * S) {
+      const int j = blk / S;
+      if (blk - j * S == 0 && j < nbb) {
+        blk = j < bps ? j : (g.ext[3] - 1) * bps + (j - bps);
+      } else {
+        const int before = min((blk + S - 1) / S, nbb);
+        blk = bps + (blk - before);
+      }
+    } else {
+      const int sl = blk / bps, r = blk - sl * bps;
+      blk = (sl == 0 ? 0 : sl == 1 ? g.ext[3] - 1 : sl - 1) * bps + r;
+    }
+  }
+  const int n = blk * SITES + (threadIdx.x - mu * SITES);
   if (n >= (int)g.vol) return;
   // site decode (row walk, even x0 first)
   const int e0 = g.ext[0], ne0 = g.ne0;
@@ -275,6 +306,23 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     for (int k = 0; k < 9; ++k) {
       if (FLAGS & 2) __stcs(b + k * 32, un.e[k]);
       else b[k * 32] = un.e[k];
+    }
+    if (PUSH) {
+      const int o2 = g.ghost[2] ? (x2 == 1 ? 0 : (x2 == g.ext[2] ? 2 : 1)) : 1;
+      const int o3 = g.ghost[3] ? (x3 == 1 ? 0 : (x3 == g.ext[3] ? 2 : 1)) : 1;
+      if (o2 != 1 || o3 != 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {  // z-face, t-face, zt-corner neighbour
+          const int a = c == 1 ? 1 : o2, bb = c == 0 ? 1 : o3;
+          if ((a == 1 && bb == 1) || (c == 2 && (o2 == 1 || o3 == 1))) continue;
+          const int k = ps->nbmap[a][bb];
+          if (k < 0) continue;
+          const int pd = p + ps->delta[k];
+          cx* d = ps->peer[k] + ((pd >> 5) * 36 + mu * 9) * 32 + (pd & 31);
+#pragma unroll
+          for (int kk = 0; kk < 9; ++kk) d[kk * 32] = un.e[kk];
+        }
+      }
     }
   }
 }
@@ -375,6 +423,76 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Checkerboard sweep sub-step (one direction mu, one colour), D = 4, with the lean addressing of V4: the staple sum
+// of KHeatBath / KOverrelax (same accumulation order: nu ascending, up then down => the same bits as the generic
+// functors) followed by the single-link rule.  KIND: 0 heat bath (heat_bath.rs:73-123), 1 over-relaxation
+// (overrelaxation.rs:86-110, 158-184).  Links of the updated (mu, colour) set never enter each other's staples, so
+// neighbours are read through the non-coherent path while the own link is read and written in place.
+template <int BLOCK, int MINB, int KIND>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_sweep4_kernel(LqGeom g, cx* __restrict__ U, int mu, int parity, int flags, int or_kind, double coupling,
+                     unsigned long long seed, unsigned long long counter) {
+  const int n = blockIdx.x * BLOCK + threadIdx.x;
+  if (n >= (int)(g.vol >> 1)) return;
+  const int e0 = g.ext[0], ne0 = g.ne0, h0 = e0 >> 1;
+  int row = n / h0;
+  const int k = n - row * h0;
+  int q = row / g.ext[1];
+  const int i1 = row - q * g.ext[1];
+  row = q;
+  q = row / g.ext[2];
+  const int i2 = row - q * g.ext[2];
+  const int i3 = q;
+  const int x0 = 2 * k + ((parity + i1 + g.goff[1] + i2 + g.goff[2] + i3 + g.goff[3] + g.goff[0]) & 1);
+  const int x1 = i1 + g.ghost[1], x2 = i2 + g.ghost[2], x3 = i3 + g.ghost[3];
+  const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
+  const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
+  const int p = x1 * s1 + x2 * s2 + x3 * s3 + sl0;
+  const int x0p = x0 + 1 < e0 ? x0 + 1 : 0, x0m = x0 > 0 ? x0 - 1 : e0 - 1;
+  const int up0 = (x0p & 1) * ne0 + (x0p >> 1) - sl0, dn0 = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
+  const int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
+  const int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
+  const int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
+  const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
+  M3 acc = m3_zero();
+#pragma unroll 1
+  for (int j = 0; j < 3; ++j) {
+    const int nu = j + (j >= mu ? 1 : 0);  // ascending, own direction skipped
+    const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
+    {
+      M3 a = lq_ld36(U, pm, nu);
+      M3 b = lq_ld36(U, p + upn, mu);
+      M3 t = m3_mul_nd(a, b);
+      M3 c = lq_ld36(U, p, nu);
+      m3_fma_nd(acc, t, c);
+    }
+    {
+      M3 a = lq_ld36(U, p + dnn, mu);
+      M3 b = lq_ld36(U, pm + dnn, nu);
+      M3 t = m3_mul_nn(a, b);
+      M3 c = lq_ld36(U, p + dnn, nu);
+      m3_fma_dn(acc, t, c);
+    }
+  }
+  cx* own = U + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
+  M3 u;
+#pragma unroll
+  for (int kk = 0; kk < 9; ++kk) u.e[kk] = own[kk * 32];
+  M3 r;
+  if (KIND == 0) {
+    // global reference-order link index = RNG stream id (results do not depend on the decomposition)
+    const lq_i64 gi = (lq_i64)(x0 + g.goff[0]) * g.gstride[0] + (lq_i64)(i1 + g.goff[1]) * g.gstride[1] +
+                      (lq_i64)(i2 + g.goff[2]) * g.gstride[2] + (lq_i64)(i3 + g.goff[3]) * g.gstride[3];
+    LqStream rng(seed, counter, (uint64_t)(gi * 4 + mu));
+    r = lq_heat_bath_link(u, acc, coupling, rng, flags);
+  } else {
+    r = lq_overrelax_link(u, acc, or_kind);
+  }
+#pragma unroll
+  for (int kk = 0; kk < 9; ++kk) own[kk * 32] = r.e[kk];
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // launchers used by lq_capi.cu (D = 4; 32-bit element indices: fields below 2^31 elements, else the generic path)
 static inline bool lq_tuned_ok(const LqGeom& g) {
   return g.D == 4 && g.nchunk * 32 * 36 < ((lq_i64)1 << 31) && g.vol < ((lq_i64)1 << 31);
@@ -383,14 +501,36 @@ static inline cudaError_t lq_tuned_efield_step(cudaStream_t st, const LqGeom& g,
                                                int nkick) {
   constexpr int BLOCK = 128;
   lq_md4_kernel<BLOCK, 3, 0, 2><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, nullptr, E, coef, dt,
-                                                                                                0.0, 0.0, nkick);
+                                                                                                0.0, 0.0, nkick, nullptr, 0);
   return cudaGetLastError();
 }
 static inline cudaError_t lq_tuned_efield_link_step(cudaStream_t st, const LqGeom& g, const cx* U, cx* Unew, cx* E,
                                                     double coef, double dt_e, double dt_u, double c_u, int nkick) {
   constexpr int BLOCK = 128;
   lq_md4_kernel<BLOCK, 3, 1, 2><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e,
-                                                                                                dt_u, c_u, nkick);
+                                                                                                dt_u, c_u, nkick, nullptr, 0);
+  return cudaGetLastError();
+}
+static inline cudaError_t lq_tuned_sweep(cudaStream_t st, const LqGeom& g, cx* U, int kind /*0 hb, 1 or*/, int mu, int parity,
+                                         int flags, int or_kind, double coupling, unsigned long long seed,
+                                         unsigned long long counter) {
+  constexpr int BLOCK = 128;
+  const unsigned nb = (unsigned)((g.vol / 2 + BLOCK - 1) / BLOCK);
+  if (kind == 0)
+    lq_sweep4_kernel<BLOCK, 3, 0><<<nb, BLOCK, 0, st>>>(g, U, mu, parity, flags, or_kind, coupling, seed, counter);
+  else
+    lq_sweep4_kernel<BLOCK, 3, 1><<<nb, BLOCK, 0, st>>>(g, U, mu, parity, flags, or_kind, coupling, seed, counter);
+  return cudaGetLastError();
+}
+// fused force + E kick + link step + halo push of the new boundary links into the neighbours' ghost layers
+static inline cudaError_t lq_tuned_efield_link_step_push(cudaStream_t st, const LqGeom& g, const cx* U, cx* Unew, cx* E,
+                                                         double coef, double dt_e, double dt_u, double c_u, int nkick,
+                                                         const LqPush* d_ps) {
+  constexpr int BLOCK = 128;
+  const lq_i64 slice = g.vol / g.ext[3];
+  const int bps = (g.ghost[3] && slice % (BLOCK / 4) == 0) ? (int)(slice / (BLOCK / 4)) : 0;
+  lq_md4_kernel<BLOCK, 3, 1, 2, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(
+      g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
   return cudaGetLastError();
 }
 

@@ -359,3 +359,37 @@ def test_snapshot_restore(backend):
     assert c.t == 8 and not np.array_equal(c.links_download(), U)
     c.restore()
     assert c.t == 5 and np.array_equal(c.links_download(), U) and np.array_equal(c.efield_download(), E)
+
+
+@pytest.mark.parametrize("ext", [[8, 8, 8, 8], [4, 6, 2, 8], [32, 4, 4, 2]])
+def test_tuned_kernels_equal_generic_kernels(backend, ext):
+    """D = 4 has hand-tuned kernels for the MD loop and the heat-bath / over-relaxation sub-steps
+    (csrc/lq_tuned.cuh); LQ_FLAG_GENERIC_KERNELS selects the dimension-generic functors instead.  Both must agree
+    with each other (to rounding of the staple summation order) and with the oracle."""
+    from lattice_qcd_rs_b200 import FLAG_GENERIC_KERNELS
+    o = Oracle(4, ext, a=1.0, beta=6.0)
+    U = hot(o)
+    E = o.momenta_refresh(SEED_RNG, 7)
+    Uo, Eo = o.integrate(U, E, "symplectic", 0.01, n=3)
+    Uhb = o.sweep_heatbath(U, SEED_RNG, 31)
+    Uor = o.sweep_overrelax(U, 1)
+    res = []
+    for flags in (0, FLAG_GENERIC_KERNELS):
+        c = backend(4, ext, a=1.0, beta=6.0)
+        c.set_flags(flags)
+        c.links_upload(U)
+        c.efield_upload(E)
+        c.symplectic_n(0.01, 3)
+        md = (c.links_download(), c.efield_download())
+        assert rel(md[0], Uo) <= RTOL and rel(md[1], Eo) <= RTOL
+        c.links_upload(U)
+        c.sweep_heatbath(SEED_RNG, 31)
+        hb = c.links_download()
+        assert rel(hb, Uhb) <= 1e-9
+        c.links_upload(U)
+        c.sweep_overrelax(1)
+        orx = c.links_download()
+        assert rel(orx, Uor) <= 1e-9
+        res.append((md, hb, orx))
+    assert rel(res[0][0][0], res[1][0][0]) <= 1e-14 and rel(res[0][0][1], res[1][0][1]) <= 1e-14
+    assert rel(res[0][1], res[1][1]) <= 1e-12 and rel(res[0][2], res[1][2]) <= 1e-12

@@ -201,7 +201,7 @@ int main(int argc, char** argv) {
   vs.push_back({std::string("v4 lean nu-loop block=" #BLOCK " minb=" #MINB),                                        \
                 [&] {                                                                                               \
                   lq_md4_kernel<BLOCK, MINB, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>(      \
-                      g, U, U2, E, coef, dt / 2, dt, c_u, 2);                                                       \
+                      g, U, U2, E, coef, dt / 2, dt, c_u, 2, nullptr, 0);                                             \
                   CK(cudaGetLastError());                                                                           \
                 },                                                                                                  \
                 (const void*)lq_md4_kernel<BLOCK, MINB, 1>, BLOCK})
@@ -216,7 +216,7 @@ int main(int argc, char** argv) {
                     cudaFuncSetAttribute(lq_md4_kernel<BLOCK, MINB, 1, FLAGS>,                                      \
                                          cudaFuncAttributePreferredSharedMemoryCarveout, CARVE);                   \
                   lq_md4_kernel<BLOCK, MINB, 1, FLAGS><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>( \
-                      g, U, U2, E, coef, dt / 2, dt, c_u, 2);                                                       \
+                      g, U, U2, E, coef, dt / 2, dt, c_u, 2, nullptr, 0);                                             \
                   CK(cudaGetLastError());                                                                           \
                 },                                                                                                  \
                 (const void*)lq_md4_kernel<BLOCK, MINB, 1, FLAGS>, BLOCK})
