@@ -185,34 +185,12 @@ struct LqPush {
 };
 // FLAGS: 1 = visit nu so that direction 3 (first touched from DRAM by most blocks) comes last, 2 = streaming
 // (evict-first) accesses for E and U', 4 = FAKE neighbours (perfect-locality bound, kbench only: wrong results)
-template <int BLOCK, int MINB, int FUSED, int FLAGS = 0, int PUSH = 0>
-__global__ void __launch_bounds__(BLOCK, MINB)
-    lq_md4_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef, double dt_e,
-                  double dt_u, double c_u, int nkick, const LqPush* __restrict__ ps, int bps) {
-  // ps: device-resident peer table, read by the threads of boundary slices only; bps: blocks per t-slice (0: keep
-  // the natural block order)
+template <int BLOCK, int FUSED, int FLAGS, int PUSH>
+__device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restrict__ U, cx* __restrict__ Unew,
+                                            cx* __restrict__ E, double coef, double dt_e, double dt_u, double c_u,
+                                            int nkick, const LqPush* __restrict__ ps, int blk) {
   constexpr int SITES = BLOCK / 4;
   const int mu = threadIdx.x / SITES;
-  int blk = blockIdx.x;
-  if (PUSH && bps) {
-    // The blocks of the two boundary t-slices are interleaved 1 : (S-1) with interior blocks over the first part of
-    // the grid: their NVLink stores are spread over S times their own compute time instead of saturating the link
-    // in one burst, and everything has landed long before the kernel ends.  (ext3 < 2S: first, last, interior.)
-    constexpr int S = 4;
-    const int nbb = 2 * bps;
-    if (g.ext[3] >= 2 * S) {
-      const int j = blk / S;
-      if (blk - j * S == 0 && j < nbb) {
-        blk = j < bps ? j : (g.ext[3] - 1) * bps + (j - bps);
-      } else {
-        const int before = min((blk + S - 1) / S, nbb);
-        blk = bps + (blk - before);
-      }
-    } else {
-      const int sl = blk / bps, r = blk - sl * bps;
-      blk = (sl == 0 ? 0 : sl == 1 ? g.ext[3] - 1 : sl - 1) * bps + r;
-    }
-  }
   const int n = blk * SITES + (threadIdx.x - mu * SITES);
   if (n >= (int)g.vol) return;
   // site decode (row walk, even x0 first)
@@ -325,6 +303,46 @@ __global__ void __launch_bounds__(BLOCK, MINB)
       }
     }
   }
+}
+
+// FLAGS & 16: persistent walk -- the grid is a few blocks per SM and every block walks a CONTIGUOUS range of rows,
+// so the +-x1 neighbour rows of a row were touched by the same SM a moment ago (L1 hits instead of L2 round trips).
+template <int BLOCK, int MINB, int FUSED, int FLAGS = 0, int PUSH = 0>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_md4_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef, double dt_e,
+                  double dt_u, double c_u, int nkick, const LqPush* __restrict__ ps, int bps) {
+  // ps: device-resident peer table, read by the threads of boundary slices only; bps: blocks per t-slice (0: keep
+  // the natural block order)
+  if (FLAGS & 16) {
+    constexpr int SITES = BLOCK / 4;
+    const int nblk = ((int)g.vol + SITES - 1) / SITES;
+    const int per = (nblk + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int b0 = blockIdx.x * per, b1 = min(b0 + per, nblk);
+#pragma unroll 1
+    for (int b = b0; b < b1; ++b) lq_md4_body<BLOCK, FUSED, FLAGS, 0>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, ps, b);
+    return;
+  }
+  int blk = blockIdx.x;
+  if (PUSH && bps) {
+    // The blocks of the two boundary t-slices are interleaved 1 : (S-1) with interior blocks over the first part of
+    // the grid: their NVLink stores are spread over S times their own compute time instead of saturating the link
+    // in one burst, and everything has landed long before the kernel ends.  (ext3 < 2S: first, last, interior.)
+    constexpr int S = 4;
+    const int nbb = 2 * bps;
+    if (g.ext[3] >= 2 * S) {
+      const int j = blk / S;
+      if (blk - j * S == 0 && j < nbb) {
+        blk = j < bps ? j : (g.ext[3] - 1) * bps + (j - bps);
+      } else {
+        const int before = min((blk + S - 1) / S, nbb);
+        blk = bps + (blk - before);
+      }
+    } else {
+      const int sl = blk / bps, r = blk - sl * bps;
+      blk = (sl == 0 ? 0 : sl == 1 ? g.ext[3] - 1 : sl - 1) * bps + r;
+    }
+  }
+  lq_md4_body<BLOCK, FUSED, FLAGS, PUSH>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, ps, blk);
 }
 
 // ------------------------------------------------------------------------------------------------------------

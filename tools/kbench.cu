@@ -220,6 +220,21 @@ int main(int argc, char** argv) {
                   CK(cudaGetLastError());                                                                           \
                 },                                                                                                  \
                 (const void*)lq_md4_kernel<BLOCK, MINB, 1, FLAGS>, BLOCK})
+#define V4P(BLOCK, MINB, FLAGS, GRID)                                                                              \
+  vs.push_back({std::string("v4 persistent block=" #BLOCK " minb=" #MINB " flags=" #FLAGS " grid=" #GRID),        \
+                [&] {                                                                                               \
+                  lq_md4_kernel<BLOCK, MINB, 1, FLAGS><<<GRID, BLOCK>>>(g, U, U2, E, coef, dt / 2, dt, c_u, 2,     \
+                                                                       nullptr, 0);                                \
+                  CK(cudaGetLastError());                                                                           \
+                },                                                                                                  \
+                (const void*)lq_md4_kernel<BLOCK, MINB, 1, FLAGS>, BLOCK})
+  V4P(128, 3, 18, 444);
+  V4P(128, 3, 18, 888);
+  V4P(128, 3, 18, 1776);
+  V4P(128, 3, 18, 3552);
+  V4P(128, 3, 18, 8192);
+  V4P(256, 1, 18, 148);
+  V4P(256, 1, 18, 592);
   V4F(128, 3, 2, -1);
   V4F(128, 3, 8, -1);
   V4F(128, 3, 10, -1);
