@@ -920,8 +920,27 @@ static int gauss_field(lq_ctx* c) {
   LQ_TRY(ensure_buf(&c->G, c->g_bytes(), c));
   LQ_TRY(ensure_halo(c, 0));
   LQ_TRY(ensure_halo(c, 1));
+#ifndef LQ_HOST_EMU
+  if (c->p2p_on && c->d_push) {
+    // compute + halo push in one kernel: boundary sites of G go straight into the neighbours' ghost layers
+    int bi = -1;
+    for (int b = 0; b < LQ_P2P_NBUF - 1; ++b)
+      if (c->own[b] == c->G) bi = b;
+    if (bi < 0) return LQ_E_COMM;
+    LQ_TRY(p2p_barrier(c));
+    {
+      ProfScope ps(c, LQ_PROF_GAUSS_FIELD);
+      LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussField<DD>{c->g, c->U, c->E, c->G, (const LqPush*)c->d_push + bi}))));
+    }
+    LQ_TRY(p2p_barrier(c));
+    c->p2p_exchanges++;
+    c->halo_ok[2] = true;
+    c->g_valid = true;
+    return LQ_OK;
+  }
+#endif
   ProfScope ps(c, LQ_PROF_GAUSS_FIELD);
-  LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussField<DD>{c->g, c->U, c->E, c->G}))));
+  LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussField<DD>{c->g, c->U, c->E, c->G, nullptr}))));
   c->halo_ok[2] = false;
   c->g_valid = true;
   return LQ_OK;
@@ -1373,25 +1392,24 @@ int lq_p2p_attach(lq_ctx* c, int n_peers, const void* peer_handles, int n_neighb
   }
   c->p2p_nnb = n_neighbors;
   c->p2p_epoch = 0;
-#ifdef LQ_TUNED
-  if (c->g.D == 4) {  // peer tables of the fused "compute + halo push" MD kernel, one per buffer allocation
+  if (c->g.svol * 36 < ((lq_i64)1 << 31)) {  // peer tables of the fused "compute + halo push" kernels, one per buffer
+    const int D = c->g.D;
     LqPush tab[LQ_P2P_NBUF - 1];
     memset(tab, 0, sizeof(tab));
     for (int b = 0; b < LQ_P2P_NBUF - 1; ++b) {
       for (int i = 0; i < 9; ++i) (&tab[b].nbmap[0][0])[i] = -1;
       for (int k = 0; k < n_neighbors; ++k) {
         lq_i64 delta = 0;
-        for (int d = 0; d < c->g.D; ++d) delta -= (lq_i64)c->p2p_off[k][d] * c->g.ext[d] * c->g.sstride[d];
+        for (int d = 0; d < D; ++d) delta -= (lq_i64)c->p2p_off[k][d] * c->g.ext[d] * c->g.sstride[d];
         tab[b].peer[k] = (cx*)c->p2p_base[c->p2p_peer[k]][b];
         tab[b].delta[k] = (int)delta;
-        tab[b].nbmap[c->p2p_off[k][2] + 1][c->p2p_off[k][3] + 1] = k;
+        tab[b].nbmap[(D >= 3 ? c->p2p_off[k][D - 2] : 0) + 1][c->p2p_off[k][D - 1] + 1] = k;
       }
     }
     if (!c->d_push) LQ_TRY(rt_malloc(&c->d_push, sizeof(tab)));
     LQ_TRY(rt_copy(c->d_push, tab, sizeof(tab), H2D, c->stream));
     LQ_TRY(rt_sync(c->stream));
   }
-#endif
   c->p2p_on = true;
   return LQ_OK;
 #endif

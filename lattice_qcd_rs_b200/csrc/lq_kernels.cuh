@@ -391,6 +391,23 @@ struct KReunitarize {  // LinkMatrix::normalize, field.rs:897-901 -> orthonormal
   }
 };
 
+// Peer table of the fused "compute + halo push" kernels (decomposed contexts with the peer-to-peer transport):
+// threads that own an element of a boundary slice also store it straight into the ghost layer of the neighbour
+// rank(s) over NVLink.  The stores are posted, so the transfer overlaps the arithmetic of the other blocks.
+struct LqPush {
+  cx* peer[8];      // neighbour k's buffer (the allocation that corresponds to the one being written)
+  int delta[8];     // slot shift into its ghost layer
+  int nbmap[3][3];  // [o_a + 1][o_b + 1] -> neighbour index or -1; o = neighbour offset in directions D-2, D-1
+};
+// which boundary (if any) of the two splittable directions a storage site sits on: 0 low, 1 none, 2 high
+template <int D>
+LQ_HD void lq_boundary_code(const LqGeom& g, const Site<D>& x, int& oa, int& ob) {
+  oa = 1;
+  ob = 1;
+  if (D >= 3 && g.ghost[D - 2]) oa = x.x[D - 2] == 1 ? 0 : (x.x[D - 2] == g.ext[D - 2] ? 2 : 1);
+  if (g.ghost[D - 1]) ob = x.x[D - 1] == 1 ? 0 : (x.x[D - 1] == g.ext[D - 1] ? 2 : 1);
+}
+
 // ---------------------------------------------------------------------------------------------- Gauss law
 // EField::gauss, field.rs:1174-1195:  G(x) = sum_i [ E_i(x) - U_i^+(x-i) E_i(x-i) U_i(x-i) ]
 template <int D>
@@ -419,11 +436,26 @@ struct KGaussField {
   const cx* U;
   const cx* E;
   cx* G;
+  const LqPush* ps;  // non-null: also store boundary sites into the neighbours' ghost layers (fused halo push)
   LQ_HD void operator()(lq_i64 n) const {
     Site<D> x = lq_site<D>(g, n);
     M3 m = lq_gauss_site<D>(U, E, g, x);
     lq_i64 p = lq_slot<D>(g, x);
     lq_store_g(G, p, m);
+    if (ps) {
+      int oa, ob;
+      lq_boundary_code<D>(g, x, oa, ob);
+      if (oa != 1 || ob != 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {  // face a, face b, corner
+          const int a = c == 1 ? 1 : oa, b = c == 0 ? 1 : ob;
+          if ((a == 1 && b == 1) || (c == 2 && (oa == 1 || ob == 1))) continue;
+          const int k = ps->nbmap[a][b];
+          if (k < 0) continue;
+          lq_store_g(ps->peer[k], p + ps->delta[k], m);
+        }
+      }
+    }
   }
 };
 template <int D>

@@ -252,17 +252,43 @@ LQ_HD M2 lq_heat_bath_su2(const M2& stap, double coupling, LqStream& rng, int fl
   }
   return lq_random_su2(rng);
 }
-// HeatBathSweep::get_modif, heat_bath.rs:90-109: Cabibbo-Marinari over the r, s, t SU(2) blocks.
+// get_r/s/t and get_sub_block_* with a RUN-TIME block index, written with selects so that the matrices stay in
+// registers when the three sub-group updates below share one (non-unrolled) loop body.
+LQ_HD cx lq_sel3(int which, cx v0, cx v1, cx v2) { return which == 0 ? v0 : (which == 1 ? v1 : v2); }
+LQ_HD M2 lq_sub_block_rt(const M3& m, int which) {
+  M2 r;  // blocks (0,1), (0,2), (1,2)
+  r.a = lq_sel3(which, m.e[0], m.e[0], m.e[4]);
+  r.b = lq_sel3(which, m.e[1], m.e[2], m.e[5]);
+  r.c = lq_sel3(which, m.e[3], m.e[6], m.e[7]);
+  r.d = lq_sel3(which, m.e[4], m.e[8], m.e[8]);
+  return r;
+}
+LQ_HD M3 lq_embed_rt(const M2& m, int which) {
+  const cx one = cmk(1.0, 0.0), zero = cmk(0.0, 0.0);
+  M3 r;
+  r.e[0] = lq_sel3(which, m.a, m.a, one);
+  r.e[1] = lq_sel3(which, m.b, zero, zero);
+  r.e[2] = lq_sel3(which, zero, m.b, zero);
+  r.e[3] = lq_sel3(which, m.c, zero, zero);
+  r.e[4] = lq_sel3(which, m.d, one, m.a);
+  r.e[5] = lq_sel3(which, zero, zero, m.b);
+  r.e[6] = lq_sel3(which, zero, m.c, zero);
+  r.e[7] = lq_sel3(which, zero, zero, m.c);
+  r.e[8] = lq_sel3(which, one, m.d, m.d);
+  return r;
+}
+// HeatBathSweep::get_modif, heat_bath.rs:90-109: Cabibbo-Marinari over the r, s, t SU(2) blocks:
+//   r = R(U A), s = S(r U A), t = T(s r U A), U' = t s r U -- one loop body executed three times (a third of the
+//   code of the unrolled form: the sampler with its Philox rounds, log and cos is instantiated once).
 LQ_HD M3 lq_heat_bath_link(const M3& u, const M3& a, double coupling, LqStream& rng, int flags) {
-  M3 w = m3_mul_nn(u, a);
-  M3 r = lq_embed(lq_heat_bath_su2(lq_project_to_su2_unorm(lq_sub_block(w, 0)), coupling, rng, flags), 0);
-  M3 ru = m3_mul_nn(r, u);
-  w = m3_mul_nn(ru, a);
-  M3 s = lq_embed(lq_heat_bath_su2(lq_project_to_su2_unorm(lq_sub_block(w, 1)), coupling, rng, flags), 1);
-  M3 sru = m3_mul_nn(s, ru);
-  w = m3_mul_nn(sru, a);
-  M3 t = lq_embed(lq_heat_bath_su2(lq_project_to_su2_unorm(lq_sub_block(w, 2)), coupling, rng, flags), 2);
-  return m3_mul_nn(t, sru);
+  M3 cur = u;
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {
+    M3 w = m3_mul_nn(cur, a);
+    M3 x = lq_embed_rt(lq_heat_bath_su2(lq_project_to_su2_unorm(lq_sub_block_rt(w, which)), coupling, rng, flags), which);
+    cur = m3_mul_nn(x, cur);
+  }
+  return cur;
 }
 // MetropolisHastingsSweep::potential_modif, metropolis_hastings_sweep.rs:126-143
 LQ_HD M3 lq_metropolis_proposal(const M3& old_link, int n_update, double spread, LqStream& rng, int flags) {

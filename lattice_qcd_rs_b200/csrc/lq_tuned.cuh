@@ -174,15 +174,6 @@ __device__ __forceinline__ M3 lq_ld36(const cx* __restrict__ U, int slot, int di
   for (int k = 0; k < 9; ++k) r.e[k] = __ldg(b + k * 32);
   return r;
 }
-// Peer table of the fused "compute + halo push" variant (PUSH = 1, decomposed contexts with the peer-to-peer
-// transport): threads that own a link of a boundary slice also store the new link straight into the ghost layer of
-// the neighbour rank(s) over NVLink.  The stores are posted, so the transfer overlaps the arithmetic of the other
-// blocks; with `bps` set the two boundary t-slices are walked first and the interior hides the whole transfer.
-struct LqPush {
-  cx* peer[8];            // neighbour k's link buffer (the allocation our Unew corresponds to)
-  int delta[8];           // slot shift into its ghost layer
-  int nbmap[3][3];        // [o_z + 1][o_t + 1] -> neighbour index or -1 (o = offset of the neighbour in directions 2, 3)
-};
 // FLAGS: 1 = visit nu so that direction 3 (first touched from DRAM by most blocks) comes last, 2 = streaming
 // (evict-first) accesses for E and U', 4 = FAKE neighbours (perfect-locality bound, kbench only: wrong results)
 template <int BLOCK, int FUSED, int FLAGS, int PUSH>
