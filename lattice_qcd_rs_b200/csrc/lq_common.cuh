@@ -30,11 +30,13 @@ struct double2 {
 };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #define LQ_HD inline
+#define LQ_NOINLINE static
 #define LQ_LDG(p) (*(p))
 #define LQ_RESTRICT
 #else
 #include <cuda_runtime.h>
 #define LQ_HD __host__ __device__ __forceinline__
+#define LQ_NOINLINE static __host__ __device__ __noinline__
 #ifdef __CUDA_ARCH__
 #define LQ_LDG(p) __ldg(p)
 #else
@@ -280,7 +282,11 @@ LQ_HD M3 m3_cscale(const M3& a, cx s) {
   for (int k = 0; k < 9; ++k) r.e[k] = cmul(a.e[k], s);
   return r;
 }
-// acc += A*B
+// acc += A*B.  -DLQ_MATMUL_KOUTER selects a k-outermost two-pass ordering of the same FMAs (every accumulator sees
+// the same sequence, so the bits are identical) that puts 18 independent chains between two dependent DFMAs; ptxas
+// schedules the plain source order at least as well (measured: 0.655 vs 0.672 ms for the fused MD kernel), so it
+// stays an experiment switch.
+#ifndef LQ_MATMUL_KOUTER
 LQ_HD void m3_fma_nn(M3& acc, const M3& a, const M3& b) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -289,7 +295,6 @@ LQ_HD void m3_fma_nn(M3& acc, const M3& a, const M3& b) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) cfma(acc.e[3 * i + j], a.e[3 * i + k], b.e[3 * k + j]);
 }
-// acc += A*B^dagger
 LQ_HD void m3_fma_nd(M3& acc, const M3& a, const M3& b) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -298,7 +303,6 @@ LQ_HD void m3_fma_nd(M3& acc, const M3& a, const M3& b) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) cfma_c(acc.e[3 * i + j], a.e[3 * i + k], b.e[3 * j + k]);
 }
-// acc += A^dagger*B
 LQ_HD void m3_fma_dn(M3& acc, const M3& a, const M3& b) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -307,6 +311,73 @@ LQ_HD void m3_fma_dn(M3& acc, const M3& a, const M3& b) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) cfma_ca(acc.e[3 * i + j], a.e[3 * k + i], b.e[3 * k + j]);
 }
+#else
+LQ_HD void m3_fma_nn(M3& acc, const M3& a, const M3& b) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const cx x = a.e[3 * i + k], y = b.e[3 * k + j];
+        acc.e[3 * i + j].x = fma(x.x, y.x, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = fma(x.x, y.y, acc.e[3 * i + j].y);
+      }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const cx x = a.e[3 * i + k], y = b.e[3 * k + j];
+        acc.e[3 * i + j].x = fma(-x.y, y.y, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = fma(x.y, y.x, acc.e[3 * i + j].y);
+      }
+  }
+}
+// acc += A*B^dagger
+LQ_HD void m3_fma_nd(M3& acc, const M3& a, const M3& b) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const cx x = a.e[3 * i + k], y = b.e[3 * j + k];
+        acc.e[3 * i + j].x = fma(x.x, y.x, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = fma(x.y, y.x, acc.e[3 * i + j].y);
+      }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const cx x = a.e[3 * i + k], y = b.e[3 * j + k];
+        acc.e[3 * i + j].x = fma(x.y, y.y, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = fma(-x.x, y.y, acc.e[3 * i + j].y);
+      }
+  }
+}
+// acc += A^dagger*B
+LQ_HD void m3_fma_dn(M3& acc, const M3& a, const M3& b) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const cx x = a.e[3 * k + i], y = b.e[3 * k + j];
+        acc.e[3 * i + j].x = fma(x.x, y.x, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = fma(x.x, y.y, acc.e[3 * i + j].y);
+      }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const cx x = a.e[3 * k + i], y = b.e[3 * k + j];
+        acc.e[3 * i + j].x = fma(x.y, y.y, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = fma(-x.y, y.x, acc.e[3 * i + j].y);
+      }
+  }
+}
+#endif
 LQ_HD M3 m3_mul_nn(const M3& a, const M3& b) {
   M3 r = m3_zero();
   m3_fma_nn(r, a, b);
