@@ -112,6 +112,12 @@ int lq_hamiltonian_links(lq_ctx*, double* h);      /* state.rs:821-849  */
 int lq_hamiltonian_efield(lq_ctx*, double* h);     /* state.rs:1370-1385 */
 int lq_hamiltonian_total(lq_ctx*, double* h);      /* state.rs:229-231  */
 
+/* field-strength observables on every site (n_sites * 18, reference AoS).  Signed directions: +(d+1) / -(d+1).
+ * LinkMatrix::clover (field.rs:807-820), f_mu_nu (:825-835), magnetic_field (:851-874). */
+int lq_clover(lq_ctx*, int sdir_i, int sdir_j, double* aos_out, int64_t n_sites);
+int lq_f_mu_nu(lq_ctx*, int dir_i, int dir_j, double* aos_out, int64_t n_sites);
+int lq_magnetic_field(lq_ctx*, int dir, double* aos_out, int64_t n_sites);
+
 /* ---- molecular dynamics ------------------------------------------------------------------------------------ */
 int lq_staples(lq_ctx*, double* aos_out, int64_t n_links);   /* staple(), monte_carlo/mod.rs:339-362 (parity/debug) */
 int lq_force(lq_ctx*, double* aos_out, int64_t n_links);     /* derivative_e, state.rs:1420-1448 (dE/dt, no update) */

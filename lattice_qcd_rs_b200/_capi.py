@@ -78,6 +78,9 @@ SYMBOLS = {
     "lq_hamiltonian_links": (C.c_int, [_vp, _dp]),
     "lq_hamiltonian_efield": (C.c_int, [_vp, _dp]),
     "lq_hamiltonian_total": (C.c_int, [_vp, _dp]),
+    "lq_clover": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int64]),
+    "lq_f_mu_nu": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int64]),
+    "lq_magnetic_field": (C.c_int, [_vp, C.c_int, _dp, C.c_int64]),
     "lq_staples": (C.c_int, [_vp, _dp, C.c_int64]),
     "lq_force": (C.c_int, [_vp, _dp, C.c_int64]),
     "lq_efield_step": (C.c_int, [_vp, C.c_double]),
@@ -331,6 +334,22 @@ class Context:
 
     def hamiltonian_total(self):
         return self._scalar(self.lib.lq_hamiltonian_total, "lq_hamiltonian_total")
+
+    # -- field-strength observables (signed directions: +(d+1) / -(d+1))
+    def clover(self, sdir_i, sdir_j):
+        out = np.empty((self.ns, 18))
+        self._check(self.lib.lq_clover(self._h, sdir_i, sdir_j, _p(out), self.ns), "lq_clover")
+        return out
+
+    def f_mu_nu(self, dir_i, dir_j):
+        out = np.empty((self.ns, 18))
+        self._check(self.lib.lq_f_mu_nu(self._h, dir_i, dir_j, _p(out), self.ns), "lq_f_mu_nu")
+        return out
+
+    def magnetic_field(self, direction):
+        out = np.empty((self.ns, 18))
+        self._check(self.lib.lq_magnetic_field(self._h, direction, _p(out), self.ns), "lq_magnetic_field")
+        return out
 
     # -- molecular dynamics
     def staples(self):

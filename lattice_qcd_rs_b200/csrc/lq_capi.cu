@@ -676,7 +676,7 @@ int lq_links_set_random(lq_ctx* c, uint64_t seed, uint64_t counter) {
 static int plaquette_all(lq_ctx* c, double v[3]) {
   LQ_TRY(ensure_halo(c, 0));
   ProfScope ps(c, LQ_PROF_PLAQUETTE);
-  LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol, KPlaquette<DD>{c->g, c->U, c->CA}))));
+  LQ_DISPATCH(c, LQ_TRY((reduce(c, KPlaquette<DD>::items(c->g), KPlaquette<DD>{c->g, c->U, c->CA}))));
   for (int k = 0; k < 3; ++k) v[k] = c->h_result[k];
   return global_sum(c, v, 3);
 }
@@ -722,6 +722,32 @@ int lq_hamiltonian_total(lq_ctx* c, double* h) {
   LQ_TRY(lq_hamiltonian_efield(c, &b));
   *h = a + b;
   return LQ_OK;
+}
+
+// field-strength observables (SURVEY section 8f "next": same stencil machinery, golden vectors field.rs:1580-1711)
+static int field_strength(lq_ctx* c, int mode, int p0, int p1, double* aos_out, int64_t n_sites) {
+  if (!c || !aos_out) return LQ_E_BADARG;
+  if (n_sites != c->g.vol) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  size_t bytes = (size_t)n_sites * 18 * sizeof(double);
+  LQ_TRY(ensure_aos(c, bytes));
+  LQ_TRY(ensure_halo(c, 0));
+  LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KFieldStrength<DD>{c->g, c->U, c->d_aos, mode, p0, p1, c->a}))));
+  LQ_TRY(rt_copy(aos_out, c->d_aos, bytes, D2H, c->stream));
+  return rt_sync(c->stream);
+}
+static bool signed_dir_ok(const lq_ctx* c, int sd) { return c && sd != 0 && abs(sd) <= c->g.D; }
+int lq_clover(lq_ctx* c, int sdir_i, int sdir_j, double* aos_out, int64_t n_sites) {
+  if (!signed_dir_ok(c, sdir_i) || !signed_dir_ok(c, sdir_j)) return LQ_E_BADARG;
+  return field_strength(c, 0, sdir_i, sdir_j, aos_out, n_sites);
+}
+int lq_f_mu_nu(lq_ctx* c, int dir_i, int dir_j, double* aos_out, int64_t n_sites) {
+  if (!c || dir_i < 0 || dir_j < 0 || dir_i >= c->g.D || dir_j >= c->g.D) return LQ_E_BADARG;
+  return field_strength(c, 1, dir_i, dir_j, aos_out, n_sites);
+}
+int lq_magnetic_field(lq_ctx* c, int dir, double* aos_out, int64_t n_sites) {
+  if (!c || dir < 0 || dir >= c->g.D) return LQ_E_BADARG;
+  return field_strength(c, 2, dir, 0, aos_out, n_sites);
 }
 
 // ---------------------------------------------------------------------------------------------- molecular dynamics

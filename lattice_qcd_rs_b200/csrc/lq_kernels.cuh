@@ -201,32 +201,44 @@ struct KMomentaRefresh {  // EField::new_determinist with Normal(0, sigma), fiel
 // average_trace_plaquette (field.rs:775-804) and hamiltonian_links (state.rs:821-849) in one pass:
 //   v[0] += Re sum_{i<j} Tr P_ij(x); v[1] += Im ...; v[2] += sum_{i<j} (1 - Re Tr P_ij(x)/CA)
 // P_ij(x) = U_i(x) U_j(x+i) U_i^+(x+j) U_j^+(x)  (pij/sij, field.rs:743-771)
+// One item per (site, plane): groups of 32 consecutive sites x D(D-1)/2 planes, so a warp walks 32 consecutive
+// sites of one plane (coalesced) and the warps of a block share the links of their sites through L1.
 template <int D>
 struct KPlaquette {
   static constexpr int K = 3;
+  static constexpr int NPL = D * (D - 1) / 2;
   LqGeom g;
   const cx* U;
   double CA;
-  LQ_HD void operator()(lq_i64 n, double* v) const {
-    Site<D> x = lq_site<D>(g, n);
-    double sre = 0.0, sim = 0.0, sh = 0.0;
+  static LQ_HD lq_i64 items(const LqGeom& g) { return ((g.vol + 31) / 32) * 32 * NPL; }
+  LQ_HD void operator()(lq_i64 it, double* v) const {
+    lq_i64 blk = it / (32 * NPL);
+    int r = (int)(it - blk * (32 * NPL));
+    int pl = r >> 5;
+    lq_i64 n = blk * 32 + (r & 31);
+    if (n >= g.vol) return;
+    // plane index -> (i < j), planes ordered (0,1), (0,2), ..., (1,2), ... as the reference's double loop
+    int i = 0, j = 1, cnt = 0;
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      Site<D> xpi = lq_up<D>(g, x, i);
+    for (int a = 0; a < D; ++a)
 #pragma unroll
-      for (int j = i + 1; j < D; ++j) {
-        Site<D> xpj = lq_up<D>(g, x, j);
-        M3 a = m3_mul_nn(lq_load_link(U, g, i, lq_slot<D>(g, x)), lq_load_link(U, g, j, lq_slot<D>(g, xpi)));
-        M3 b = m3_mul_nn(lq_load_link(U, g, j, lq_slot<D>(g, x)), lq_load_link(U, g, i, lq_slot<D>(g, xpj)));
-        cx t = m3_trace_nd(a, b);
-        sre += t.x;
-        sim += t.y;
-        sh += 1.0 - t.x / CA;
+      for (int b = a + 1; b < D; ++b) {
+        if (cnt == pl) {
+          i = a;
+          j = b;
+        }
+        ++cnt;
       }
-    }
-    v[0] += sre;
-    v[1] += sim;
-    v[2] += sh;
+    Site<D> x = lq_site<D>(g, n);
+    lq_i64 p = lq_slot<D>(g, x);
+    Site<D> xpi = lq_up<D>(g, x, i);
+    Site<D> xpj = lq_up<D>(g, x, j);
+    M3 a = m3_mul_nn(lq_load_link(U, g, i, p), lq_load_link(U, g, j, lq_slot<D>(g, xpi)));
+    M3 b = m3_mul_nn(lq_load_link(U, g, j, p), lq_load_link(U, g, i, lq_slot<D>(g, xpj)));
+    cx t = m3_trace_nd(a, b);
+    v[0] += t.x;
+    v[1] += t.y;
+    v[2] += 1.0 - t.x / CA;
   }
 };
 // hamiltonian_efield (state.rs:1370-1385): sum_x sum_i trace_squared(E_i(x)) (field.rs:164-167); beta on the host
@@ -248,6 +260,84 @@ struct KEfieldEnergy {
       s += t / 2.0;
     }
     v[0] += s;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- field-strength observables
+// Signed directions: sd = +(d+1) / -(d+1).  LinkMatrix::matrix (field.rs:726-740): U_d(x) or, for a negative direction,
+// U_d^+(x - d).
+template <int D>
+LQ_HD Site<D> lq_shift_signed(const LqGeom& g, const Site<D>& x, int sd) {
+  return sd > 0 ? lq_up<D>(g, x, sd - 1) : lq_dn<D>(g, x, -sd - 1);
+}
+template <int D>
+LQ_HD M3 lq_link_signed(const cx* LQ_RESTRICT U, const LqGeom& g, const Site<D>& x, int sd) {
+  if (sd > 0) return lq_load_link(U, g, sd - 1, lq_slot<D>(g, x));
+  return m3_adj(lq_load_link(U, g, -sd - 1, lq_slot<D>(g, lq_dn<D>(g, x, -sd - 1))));
+}
+// pij, field.rs:761-771:  P_ij(x) = U_i(x) S_ij^+(x),  S_ij(x) = U_j(x) U_i(x+j) U_j^+(x+i)   (sij, :743-758)
+template <int D>
+LQ_HD M3 lq_pij_signed(const cx* LQ_RESTRICT U, const LqGeom& g, const Site<D>& x, int si, int sj) {
+  M3 u_j = lq_link_signed<D>(U, g, x, sj);
+  M3 u_i_pj = lq_link_signed<D>(U, g, lq_shift_signed<D>(g, x, sj), si);
+  M3 u_j_pi = lq_link_signed<D>(U, g, lq_shift_signed<D>(g, x, si), sj);
+  M3 s = m3_mul_nd(m3_mul_nn(u_j, u_i_pj), u_j_pi);
+  return m3_mul_nd(lq_link_signed<D>(U, g, x, si), s);
+}
+// clover, field.rs:807-820:  P_{i,j} + P_{j,-i} + P_{-i,-j} + P_{-j,i}
+template <int D>
+LQ_HD M3 lq_clover_site(const cx* LQ_RESTRICT U, const LqGeom& g, const Site<D>& x, int si, int sj) {
+  M3 r = lq_pij_signed<D>(U, g, x, si, sj);
+  r = m3_add(r, lq_pij_signed<D>(U, g, x, sj, -si));
+  r = m3_add(r, lq_pij_signed<D>(U, g, x, -si, -sj));
+  r = m3_add(r, lq_pij_signed<D>(U, g, x, -sj, si));
+  return r;
+}
+// f_mu_nu, field.rs:825-835:  (clover_ij - clover_ji) / (8 a^2)
+template <int D>
+LQ_HD M3 lq_fmunu_site(const cx* LQ_RESTRICT U, const LqGeom& g, const Site<D>& x, int i, int j, double a) {
+  M3 m = m3_sub(lq_clover_site<D>(U, g, x, i + 1, j + 1), lq_clover_site<D>(U, g, x, j + 1, i + 1));
+  const double sc = 8.0 * a * a;
+  M3 r;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.e[k] = cmk(m.e[k].x / sc, m.e[k].y / sc);
+  return r;
+}
+// levi_civita, utils.rs:306-318: product over pairs j < i of sign(index[i] - index[j])
+LQ_HD int lq_levi_civita3(int a, int b, int c) {
+  int sab = (b > a) - (b < a), sac = (c > a) - (c < a), sbc = (c > b) - (c < b);
+  return sab * sac * sbc;
+}
+// mode 0: clover(si, sj);  1: f_mu_nu(i, j) (positive directions);  2: magnetic_field(dir) (field.rs:851-874)
+template <int D>
+struct KFieldStrength {
+  LqGeom g;
+  const cx* U;
+  double* aos;
+  int mode, p0, p1;
+  double a;
+  LQ_HD void operator()(lq_i64 n) const {
+    Site<D> x = lq_site<D>(g, n);
+    M3 r;
+    if (mode == 0) {
+      r = lq_clover_site<D>(U, g, x, p0, p1);
+    } else if (mode == 1) {
+      r = lq_fmunu_site<D>(U, g, x, p0, p1, a);
+    } else {
+      M3 sum = m3_zero();
+      for (int i = 0; i < D; ++i) {
+        M3 inner = m3_zero();
+        for (int j = 0; j < D; ++j) {
+          const int lc = lq_levi_civita3(p0, i, j);
+          if (lc == 0) continue;  // the reference adds f_mn * 0 here
+          inner = m3_add(inner, m3_scale(lq_fmunu_site<D>(U, g, x, i, j, a), (double)lc));
+        }
+        sum = m3_add(sum, inner);
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) r.e[k] = cmk(sum.e[k].y / 2.0, -sum.e[k].x / 2.0);  // divided by 2i
+    }
+    lq_m3_to_aos(aos + lq_local_index<D>(g, x) * 18, r);
   }
 };
 
