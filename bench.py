@@ -263,7 +263,8 @@ def run_ours(args):
     sweeps = {}
     if world == 1:
         for name, fn, cls in (("heatbath", lambda i: ctx.sweep_heatbath(SEED, 9000 + i), "heatbath"),
-                              ("overrelax", lambda i: ctx.sweep_overrelax(0), "overrelax")):
+                              ("overrelax", lambda i: ctx.sweep_overrelax(0), "overrelax"),
+                              ("metropolis", lambda i: ctx.sweep_metropolis(SEED, 9500 + i), "metropolis")):
             fn(0)
             t = timed(fn, 3)
             sweeps[name] = {"link_updates_per_s": nl_global * 3 / (t * 1e-3), "ms_per_sweep": t / 3,
@@ -301,12 +302,22 @@ def run_ours(args):
         "breakdown_ms_per_step": {"fused_force_link_kernel": ms_fused / args.steps, "gauss_field": ms_gf / args.steps,
                                   "gauss_project_step": ms_gs / args.steps, "plaquette_reduce": ms_pl / args.steps,
                                   "total": ms / args.steps},
-        "roofline": {"bound": "hbm", "kernel": "KEfieldLinkStep<4> (force + E kick + link step)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "lq_md4_kernel<128,3,1,2> (fused force + E kick + link step" +
+                     (" + halo push into the neighbours' ghost layers)" if world > 1 else ")"), "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_link": BYTES_FUSED, "launches": n_fused,
                      "avg_launch_ms": ms_fused / max(n_fused, 1),
                      "fp64_tflops": FLOPS_FUSED * nl_local * n_fused / (ms_fused * 1e-3) / 1e12 if ms_fused > 0 else 0.0,
-                     "fp64_note": "f64 FMA pipe is the co-limiter: ~3.1 kflop per 416 algorithmic bytes (7.5 flop/B)"},
+                     "fp64_note": "f64 FMA pipe is the tighter ceiling: ~3.1 kflop per 416 algorithmic bytes = 7.6 flop/B "
+                                  "against a ridge of 5.4 flop/B (35.3 TF measured / 6.53 TB/s); frac vs HBM cannot exceed "
+                                  "0.71"},
+        "secondary_rooflines": [
+            {"kernel": "KGaussField<4> (976 B/site)", "launches": n_gf, "avg_launch_ms": ms_gf / max(n_gf, 1),
+             "achieved": 976 * (nl_local // 4) * n_gf / (ms_gf * 1e-3) / 1e9 if ms_gf > 0 else 0.0,
+             "frac": (976 * (nl_local // 4) * n_gf / (ms_gf * 1e-3) / 1e9 / peak) if ms_gf > 0 else 0.0, "unit": "GB/s"},
+            {"kernel": "KGaussProjectStep<4> (308 B/link)", "launches": n_gs, "avg_launch_ms": ms_gs / max(n_gs, 1),
+             "achieved": 308 * nl_local * n_gs / (ms_gs * 1e-3) / 1e9 if ms_gs > 0 else 0.0,
+             "frac": (308 * nl_local * n_gs / (ms_gs * 1e-3) / 1e9 / peak) if ms_gs > 0 else 0.0, "unit": "GB/s"}],
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "link-updates/s", "h2d_bytes_per_step": bytes_links,
                 "d2h_bytes_per_step": bytes_links + 64, "ms_per_step": ms_e2e / args.steps,

@@ -229,8 +229,7 @@ __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restric
 #pragma unroll
   for (int k = 0; k < 4; ++k) ev[k] = (FLAGS & 2) ? __ldcs(E + ee + k * 32) : E[ee + k * 32];
   M3 acc = m3_zero();
-#pragma unroll 1
-  for (int j = 1; j < 4; ++j) {
+  auto staple_pair = [&](int j) {
     // default: nu = mu+1, mu+2, mu+3 (mod 4); FLAGS&1: nu ascending with the own direction skipped (3 last)
     const int nu = (FLAGS & 1) ? (j - 1 + (j - 1 >= mu ? 1 : 0)) : ((mu + j) & 3);
     const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
@@ -248,6 +247,14 @@ __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restric
       M3 c = lq_ld36(U, p + dnn, nu);
       m3_fma_dn(acc, t, c);
     }
+  };
+  if (FLAGS & 64) {  // fully unrolled: the scheduler may start the loads of the next pair under the current one
+    staple_pair(1);
+    staple_pair(2);
+    staple_pair(3);
+  } else {
+#pragma unroll 1
+    for (int j = 1; j < 4; ++j) staple_pair(j);
   }
   M3 u = lq_ld36(U, p, mu);
   M3 w = m3_mul_nn(u, acc);

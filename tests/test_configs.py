@@ -191,3 +191,34 @@ def test_config5_generic_dimension(backend):
     c.reunitarize()  # the heat bath as coded leaves SU(3) (PAULI_3 quirk); HMC's Gauss projection needs unitary links
     r = c.hmc_trajectory(0.005, 5, SEED_RNG, 8)
     assert np.isfinite(r["h_new"]) and 0.0 <= r["prob"] <= 1.0
+
+
+@pytest.mark.gpu
+def test_config5_largest_single_gpu_lattice():
+    """64^4 beta = 6.2 on ONE GPU (16.8 M sites, 9.7 GB of links: the largest lattice of BASELINE.json and close to
+    the 2^31-element limit of the tuned kernels' 32-bit indices): size-independent invariants only."""
+    import torch
+    assert torch.cuda.is_available()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~45 GB of device memory")
+    from lattice_qcd_rs_b200 import Context
+    c = Context(4, 64, a=1.0, beta=6.2)
+    assert c.ns == 64 ** 4 and c.nl == 4 * 64 ** 4
+    c.links_set_cold()
+    c.efield_set_zero()
+    c.symplectic_n(0.01, 1)
+    assert c.average_trace_plaquette() == 3.0 and c.hamiltonian_total() == 0.0
+    c.links_set_random(SEED_RNG, 0)
+    p = c.average_trace_plaquette()
+    assert abs(p) < 0.01  # random SU(3): <Tr P> = 0 up to 1/sqrt(6 Ns) fluctuations
+    h = c.hamiltonian_links()
+    assert abs(h / (6.2 * 6 * c.ns) - 1.0) < 1e-3
+    c.sweep_overrelax(1)
+    assert abs(c.hamiltonian_links() - h) <= 1e-10 * abs(h)
+    c.momenta_refresh(SEED_RNG, 1)
+    h0 = c.hamiltonian_total()
+    c.symplectic_n(1e-4, 2)
+    assert abs(c.hamiltonian_total() - h0) <= 1e-6 * abs(h0) and c.t == 3
+    c.reunitarize()
+    c.close()

@@ -236,6 +236,10 @@ int main(int argc, char** argv) {
   V4P(256, 1, 18, 148);
   V4P(256, 1, 18, 592);
   V4F(128, 3, 2, -1);
+  V4F(128, 3, 66, -1);
+  V4F(128, 2, 66, -1);
+  V4F(128, 1, 66, -1);
+  V4F(256, 1, 66, -1);
   V4F(128, 3, 8, -1);
   V4F(128, 3, 10, -1);
   V4F(128, 3, 4, -1);
