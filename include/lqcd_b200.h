@@ -168,6 +168,9 @@ typedef struct lq_comm {
   void* user;
   int (*halo_exchange)(void* user, lq_ctx* ctx, int which);
   int (*allreduce_sum)(void* user, double* vals, int n);
+  /* optional (may be NULL): in-place sum of n doubles in DEVICE memory, enqueued on the context stream (e.g. one
+   * ncclAllReduce); when present every reduction costs a single host synchronisation */
+  int (*allreduce_sum_device)(void* user, double* d_vals, int n);
 } lq_comm;
 int lq_set_comm(lq_ctx*, const lq_comm* comm);
 /* run all context work on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the private one */

@@ -28,10 +28,12 @@ FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED, FLAG_GENERIC_KERNELS = 
 
 HALO_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, C.c_int)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _vp, _dp, C.c_int)
+ALLREDUCE_DEV_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, C.c_int)
 
 
 class LqComm(C.Structure):
-    _fields_ = [("user", _vp), ("halo_exchange", HALO_FN), ("allreduce_sum", ALLREDUCE_FN)]
+    _fields_ = [("user", _vp), ("halo_exchange", HALO_FN), ("allreduce_sum", ALLREDUCE_FN),
+                ("allreduce_sum_device", ALLREDUCE_DEV_FN)]
 
 
 class LqError(RuntimeError):
@@ -245,8 +247,9 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.lq_kernel_launches(self._h))
 
-    def set_comm(self, halo_exchange, allreduce_sum):
-        """halo_exchange(which) -> int, allreduce_sum(numpy view of n doubles) -> int."""
+    def set_comm(self, halo_exchange, allreduce_sum, allreduce_sum_device=None):
+        """halo_exchange(which) -> int, allreduce_sum(numpy view of n doubles) -> int,
+        allreduce_sum_device(pointer, n) -> int (optional: in-place sum in the library's result buffer)."""
         def _halo(user, ctx, which):
             try:
                 return int(halo_exchange(which) or 0)
@@ -264,7 +267,16 @@ class Context:
                 traceback.print_exc()
                 return -4
 
-        comm = LqComm(None, HALO_FN(_halo), ALLREDUCE_FN(_allr))
+        def _allr_dev(user, ptr, n):
+            try:
+                return int(allreduce_sum_device(ptr, n) or 0)
+            except Exception:
+                import traceback
+                traceback.print_exc()
+                return -4
+
+        comm = LqComm(None, HALO_FN(_halo), ALLREDUCE_FN(_allr),
+                      ALLREDUCE_DEV_FN(_allr_dev) if allreduce_sum_device is not None else ALLREDUCE_DEV_FN())
         self._comm_keepalive = comm
         self._check(self.lib.lq_set_comm(self._h, C.byref(comm)), "lq_set_comm")
 

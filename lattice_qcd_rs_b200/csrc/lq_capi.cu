@@ -117,6 +117,7 @@ struct lq_ctx {
   bool g_valid;  // the Gauss field in G matches the current (U, E)
   lq_comm comm;
   bool has_comm;
+  bool reduced_globally;  // the last reduce() result in h_result is already the global sum
   // peer-to-peer halo transport (CUDA IPC mappings of the neighbours' buffers, written over NVLink by our kernels)
   bool p2p_on;
   cx* own[LQ_P2P_NBUF - 1];                       // the six field allocations in export order: U U2 E E2 G G2
@@ -204,6 +205,11 @@ static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
     for (int k = 0; k < F::K; ++k) acc[k] += v[k];
   }
   for (int k = 0; k < F::K; ++k) c->h_result[k] = acc[k];
+  c->reduced_globally = false;
+  if (c->decomposed && c->has_comm && c->comm.allreduce_sum_device) {
+    if (c->comm.allreduce_sum_device(c->comm.user, c->h_result, F::K)) return LQ_E_COMM;
+    c->reduced_globally = true;
+  }
   return LQ_OK;
 }
 #else
@@ -281,9 +287,27 @@ static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
   lq_final_k<K><<<1, LQ_RBLOCK, 0, c->stream>>>(c->d_partial, nb, c->d_result);
   c->launches += 2;
   LQ_CHECK(cudaGetLastError());
+  // decomposed contexts: the global sum is taken on the DEVICE buffer, stream-ordered (one NCCL all-reduce enqueued by
+  // the caller's plumbing), so a reduction costs one host synchronisation in total
+  c->reduced_globally = false;
+  if (c->decomposed && c->has_comm && c->comm.allreduce_sum_device) {
+    if (c->comm.allreduce_sum_device(c->comm.user, c->d_result, K)) return LQ_E_COMM;
+    c->reduced_globally = true;
+  }
   int rc = rt_copy(c->h_result, c->d_result, K * sizeof(double), D2H, c->stream);
   if (rc) return rc;
-  return rt_sync(c->stream);
+  if (c->p2p_on) {
+    LQ_CHECK(cudaMemcpyAsync(&c->h_result[15], c->p2p_flags + LQ_P2P_MAXNB, sizeof(double), cudaMemcpyDeviceToHost,
+                             c->stream));
+  }
+  rc = rt_sync(c->stream);
+  if (rc) return rc;
+  if (c->p2p_on) {  // a flag wait that timed out (a neighbour died or left the SPMD sequence) latched an error word
+    unsigned long long err;
+    memcpy(&err, &c->h_result[15], sizeof(err));
+    if (err) return LQ_E_COMM;
+  }
+  return LQ_OK;
 }
 #endif
 
@@ -321,14 +345,10 @@ static int ensure_halo(lq_ctx* c, int which) {
 }
 static int global_sum(lq_ctx* c, double* v, int n) {
   if (!c->decomposed) return LQ_OK;
-#ifndef LQ_HOST_EMU
-  if (c->p2p_on) {  // a flag wait that timed out (a neighbour died or left the SPMD sequence) latched an error word
-    unsigned long long err = 0;
-    LQ_CHECK(cudaMemcpyAsync(&err, c->p2p_flags + LQ_P2P_MAXNB, sizeof(err), cudaMemcpyDeviceToHost, c->stream));
-    LQ_TRY(rt_sync(c->stream));
-    if (err) return LQ_E_COMM;
+  if (c->reduced_globally) {  // reduce() already summed over the ranks on the device
+    c->reduced_globally = false;
+    return LQ_OK;
   }
-#endif
   if (!c->has_comm || !c->comm.allreduce_sum) return LQ_OK;  // rank-local partial sums
   return c->comm.allreduce_sum(c->comm.user, v, n) ? LQ_E_COMM : LQ_OK;
 }

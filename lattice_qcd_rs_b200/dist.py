@@ -62,12 +62,13 @@ class DistContext:
             # all library work is ordered on torch's current stream, which torch's NCCL ops synchronise with
             self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._bufs = {}
+        self._views = {}
         self._scratch = torch.zeros(16, dtype=torch.float64, device=self.device)
         self.halo_exchanges = 0
         self.halo_bytes_sent = 0
         self.transport = "none"
         if self.world > 1:
-            self.ctx.set_comm(self._halo_exchange, self._allreduce_sum)
+            self.ctx.set_comm(self._halo_exchange, self._allreduce_sum, self._allreduce_sum_device)
             self.transport = "nccl-callbacks"
             if self.on_cuda and os.environ.get("LQ_HALO_TRANSPORT", "p2p") == "p2p":
                 self._setup_p2p()
@@ -163,6 +164,23 @@ class DistContext:
         t.copy_(torch.from_numpy(vals))
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         vals[:] = t.cpu().numpy()
+        return 0
+
+    def _allreduce_sum_device(self, ptr, n):
+        """In-place global sum of the library's own result buffer: a tensor view of that memory (device memory through
+        __cuda_array_interface__, host memory for the CPU CI), one all-reduce enqueued on the library's stream."""
+        key = (ptr, n)
+        t = self._views.get(key)
+        if t is None:
+            if self.on_cuda:
+                class _Raw:
+                    __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+                t = torch.as_tensor(_Raw(), device=self.device)
+            else:
+                import ctypes
+                t = torch.from_numpy(np.ctypeslib.as_array((ctypes.c_double * n).from_address(ptr)))
+            self._views[key] = t
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return 0
 
     # ------------------------------------------------------------------ scatter / gather of reference-order arrays
