@@ -265,41 +265,47 @@ LQ_HD M2 lq_heat_bath_su2(const M2& stap, double coupling, LqStream& rng, int fl
   }
   return lq_random_su2(rng);
 }
-// get_r/s/t and get_sub_block_* with a RUN-TIME block index, written with selects so that the matrices stay in
-// registers when the three sub-group updates below share one (non-unrolled) loop body.
-LQ_HD cx lq_sel3(int which, cx v0, cx v1, cx v2) { return which == 0 ? v0 : (which == 1 ? v1 : v2); }
-LQ_HD M2 lq_sub_block_rt(const M3& m, int which) {
-  M2 r;  // blocks (0,1), (0,2), (1,2)
-  r.a = lq_sel3(which, m.e[0], m.e[0], m.e[4]);
-  r.b = lq_sel3(which, m.e[1], m.e[2], m.e[5]);
-  r.c = lq_sel3(which, m.e[3], m.e[6], m.e[7]);
-  r.d = lq_sel3(which, m.e[4], m.e[8], m.e[8]);
-  return r;
-}
-LQ_HD M3 lq_embed_rt(const M2& m, int which) {
-  const cx one = cmk(1.0, 0.0), zero = cmk(0.0, 0.0);
-  M3 r;
-  r.e[0] = lq_sel3(which, m.a, m.a, one);
-  r.e[1] = lq_sel3(which, m.b, zero, zero);
-  r.e[2] = lq_sel3(which, zero, m.b, zero);
-  r.e[3] = lq_sel3(which, m.c, zero, zero);
-  r.e[4] = lq_sel3(which, m.d, one, m.a);
-  r.e[5] = lq_sel3(which, zero, zero, m.b);
-  r.e[6] = lq_sel3(which, zero, m.c, zero);
-  r.e[7] = lq_sel3(which, zero, zero, m.c);
-  r.e[8] = lq_sel3(which, one, m.d, m.d);
-  return r;
-}
 // HeatBathSweep::get_modif, heat_bath.rs:90-109: Cabibbo-Marinari over the r, s, t SU(2) blocks:
 //   r = R(U A), s = S(r U A), t = T(s r U A), U' = t s r U -- one loop body executed three times (a third of the
 //   code of the unrolled form: the sampler with its Philox rounds, log and cos is instantiated once).
+// Only what the rule consumes is computed: the 2x2 block (ia, ib) of W = cur * A (4 of its 9 entries), and the two
+// rows (ia, ib) of x * cur that the embedded 2x2 matrix x changes.  Every entry is the same k-ascending FMA chain as in
+// m3_mul_nn -- the skipped terms are products with the exact 0 / 1 entries of the embedding -- so the bits are those of
+// the two full 3x3 products (44 % of their FMAs).
 LQ_HD M3 lq_heat_bath_link(const M3& u, const M3& a, double coupling, LqStream& rng, int flags) {
   M3 cur = u;
 #pragma unroll 1
   for (int which = 0; which < 3; ++which) {
-    M3 w = m3_mul_nn(cur, a);
-    M3 x = lq_embed_rt(lq_heat_bath_su2(lq_project_to_su2_unorm(lq_sub_block_rt(w, which)), coupling, rng, flags), which);
-    cur = m3_mul_nn(x, cur);
+    // blocks (0,1), (0,2), (1,2): ia = which == 2, ib = 1 + (which != 0)
+    cx ra[3], rb[3], ca[3], cb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ra[k] = which == 2 ? cur.e[3 + k] : cur.e[k];
+      rb[k] = which == 0 ? cur.e[3 + k] : cur.e[6 + k];
+      ca[k] = which == 2 ? a.e[3 * k + 1] : a.e[3 * k];
+      cb[k] = which == 0 ? a.e[3 * k + 1] : a.e[3 * k + 2];
+    }
+    M2 w;
+    w.a = w.b = w.c = w.d = cmk(0.0, 0.0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      cfma(w.a, ra[k], ca[k]);
+      cfma(w.b, ra[k], cb[k]);
+      cfma(w.c, rb[k], ca[k]);
+      cfma(w.d, rb[k], cb[k]);
+    }
+    const M2 x = lq_heat_bath_su2(lq_project_to_su2_unorm(w), coupling, rng, flags);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      cx na = cmk(0.0, 0.0), nb = cmk(0.0, 0.0);
+      cfma(na, x.a, ra[j]);
+      cfma(na, x.b, rb[j]);
+      cfma(nb, x.c, ra[j]);
+      cfma(nb, x.d, rb[j]);
+      cur.e[j] = which == 2 ? cur.e[j] : na;
+      cur.e[3 + j] = which == 0 ? nb : (which == 2 ? na : cur.e[3 + j]);
+      cur.e[6 + j] = which == 0 ? cur.e[6 + j] : nb;
+    }
   }
   return cur;
 }

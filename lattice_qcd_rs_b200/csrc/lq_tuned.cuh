@@ -174,6 +174,15 @@ __device__ __forceinline__ M3 lq_ld36(const cx* __restrict__ U, int slot, int di
   for (int k = 0; k < 9; ++k) r.e[k] = __ldg(b + k * 32);
   return r;
 }
+// L2 prefetch of one link matrix of the warp (9 planes x the 128-byte lines its slots touch): a hint, two instructions per
+// thread.  The lanes of every group of 8 consecutive slots share one line per plane; lane k asks for plane k & 7, all
+// lanes for plane 8, so every (plane, line) pair is requested once or more whatever the rotation of lanes inside a row.
+__device__ __forceinline__ void lq_pf36(const cx* __restrict__ U, int slot, int dir) {
+  const int e = ((slot >> 5) * 36 + dir * 9) * 32 + (slot & 31);
+  const cx* b = U + e;
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (threadIdx.x & 7) * 32));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(b + 8 * 32));
+}
 // FLAGS: 1 = visit nu so that direction 3 (first touched from DRAM by most blocks) comes last, 2 = streaming
 // (evict-first) accesses for E and U', 4 = FAKE neighbours (perfect-locality bound, kbench only: wrong results)
 template <int BLOCK, int FUSED, int FLAGS, int PUSH>
@@ -233,6 +242,16 @@ __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restric
     // default: nu = mu+1, mu+2, mu+3 (mod 4); FLAGS&1: nu ascending with the own direction skipped (3 last)
     const int nu = (FLAGS & 1) ? (j - 1 + (j - 1 >= mu ? 1 : 0)) : ((mu + j) & 3);
     const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
+    if ((FLAGS & 32) && j < 3) {  // operands of the next pair: DRAM -> L2 while this pair is computed
+      const int n2 = (FLAGS & 1) ? (j + (j >= mu ? 1 : 0)) : ((mu + j + 1) & 3);
+      const int up2_ = lq_sel4(n2, up0, up1, up2, up3), dn2_ = lq_sel4(n2, dn0, dn1, dn2, dn3);
+      lq_pf36(U, pm, n2);
+      lq_pf36(U, p + up2_, mu);
+      lq_pf36(U, p, n2);
+      lq_pf36(U, p + dn2_, mu);
+      lq_pf36(U, pm + dn2_, n2);
+      lq_pf36(U, p + dn2_, n2);
+    }
     {  // up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)
       M3 a = lq_ld36(U, pm, nu);
       M3 b = lq_ld36(U, p + upn, mu);
@@ -444,7 +463,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 // functors) followed by the single-link rule.  KIND: 0 heat bath (heat_bath.rs:73-123), 1 over-relaxation
 // (overrelaxation.rs:86-110, 158-184).  Links of the updated (mu, colour) set never enter each other's staples, so
 // neighbours are read through the non-coherent path while the own link is read and written in place.
-template <int BLOCK, int MINB, int KIND>
+// PF: 0 none; 1 = L2 prefetch of the operands of the next nu pair; 2 = of all 19 matrices at thread start
+template <int BLOCK, int MINB, int KIND, int PF = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
     lq_sweep4_kernel(LqGeom g, cx* __restrict__ U, int mu, int parity, int flags, int or_kind, double coupling,
                      unsigned long long seed, unsigned long long counter) {
@@ -471,10 +491,29 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   const int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
   const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
   M3 acc = m3_zero();
+  auto pf_pair = [&](int j2) {
+    const int n2 = j2 + (j2 >= mu ? 1 : 0);
+    const int u2 = lq_sel4(n2, up0, up1, up2, up3), d2 = lq_sel4(n2, dn0, dn1, dn2, dn3);
+    lq_pf36(U, pm, n2);
+    lq_pf36(U, p + u2, mu);
+    lq_pf36(U, p, n2);
+    lq_pf36(U, p + d2, mu);
+    lq_pf36(U, pm + d2, n2);
+    lq_pf36(U, p + d2, n2);
+  };
+  if (PF == 2) {
+    pf_pair(1);
+    pf_pair(2);
+    lq_pf36(U, p, mu);
+  }
 #pragma unroll 1
   for (int j = 0; j < 3; ++j) {
     const int nu = j + (j >= mu ? 1 : 0);  // ascending, own direction skipped
     const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
+    if (PF == 1) {
+      if (j < 2) pf_pair(j + 1);
+      else lq_pf36(U, p, mu);
+    }
     {
       M3 a = lq_ld36(U, pm, nu);
       M3 b = lq_ld36(U, p + upn, mu);

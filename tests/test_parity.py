@@ -361,6 +361,39 @@ def test_snapshot_restore(backend):
     assert c.t == 5 and np.array_equal(c.links_download(), U) and np.array_equal(c.efield_download(), E)
 
 
+@pytest.mark.parametrize("ext", [[8, 8, 8, 8], [4, 6, 2, 8], [32, 4, 4, 2], [6, 4, 4, 4]])
+def test_gauss_iteration_variants_agree(backend, ext):
+    """project_to_gauss (field.rs:1265-1337) through both iteration forms -- projection-step kernel then Gauss-field
+    kernel (default), and the one-pass functor that recomputes the backward neighbours (LQ_FLAG_GAUSS_FUSED).  Same
+    arithmetic in the same order: E, the Gauss field left behind and the iteration count must agree with each other
+    (to the contraction choices of two different kernels) and with the oracle."""
+    from lattice_qcd_rs_b200 import FLAG_GAUSS_FUSED
+    o = Oracle(4, ext, a=1.0, beta=6.0)
+    U = hot(o)
+    E = o.momenta_refresh(SEED_RNG, 9)
+    Eo, ito = o.project_to_gauss(U, E)
+    out = []
+    for flags in (0, FLAG_GAUSS_FUSED):
+        c = backend(4, ext, a=1.0, beta=6.0)
+        c.set_flags(flags)
+        c.links_upload(U)
+        c.efield_upload(E)
+        c.gauss_project_step()
+        e1, g1 = c.efield_download(), c.gauss_field()
+        c.gauss_project_step()
+        c.gauss_project_step()
+        e3, g3 = c.efield_download(), c.gauss_field()
+        c.efield_upload(E)
+        it = c.gauss_project()
+        assert it == ito
+        ef = c.efield_download()
+        assert rel(ef, Eo) <= 1e-10
+        out.append((e1, g1, e3, g3, ef))
+    assert rel(out[0][0], o.project_to_gauss_step(U, E)) <= RTOL
+    for a, b in zip(out[0], out[1]):
+        assert rel(a, b) <= 1e-13
+
+
 @pytest.mark.parametrize("ext", [[8, 8, 8, 8], [4, 6, 2, 8], [32, 4, 4, 2]])
 def test_tuned_kernels_equal_generic_kernels(backend, ext):
     """D = 4 has hand-tuned kernels for the MD loop and the heat-bath / over-relaxation sub-steps

@@ -41,6 +41,31 @@ __global__ void dfma_peak(double* out, int iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+// FP64 rate of the 3x3 complex matrix-product code itself, operands resident in registers (no memory traffic): the
+// staple recurrence t = a b^+, acc += t c^+ of the MD kernel, REP times per thread.  MINB sets the register budget
+// (3 -> 168 registers, 12 warps/SM as lq_md4_kernel).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) mm_peak(const cx* __restrict__ in, cx* out, int reps) {
+  M3 a, b, c, acc = m3_zero();
+  const int t0 = blockIdx.x * 128 + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    a.e[k] = in[(t0 * 27 + k) & 0xfffff];
+    b.e[k] = in[(t0 * 27 + 9 + k) & 0xfffff];
+    c.e[k] = in[(t0 * 27 + 18 + k) & 0xfffff];
+  }
+#pragma unroll 1
+  for (int r = 0; r < reps; ++r) {
+    M3 t = m3_mul_nd(a, b);
+    m3_fma_nd(acc, t, c);
+    M3 t2 = m3_mul_nn(c, a);
+    m3_fma_dn(acc, t2, b);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) a.e[k].x += 1e-9 * acc.e[8 - k].y;  // keep the products loop-carried
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out[t0 * 9 + k] = acc.e[k];
+}
 // streaming copy (HBM peak on this box, double2)
 __global__ void copy_k(const double2* __restrict__ a, double2* __restrict__ b, lq_i64 n) {
   lq_i64 i = (lq_i64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,6 +135,25 @@ int main(int argc, char** argv) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     double fl = 2.0 * 8 * iters * 148.0 * 8 * 256;
     printf("FP64 FMA peak: %.2f TFLOP/s (%.3f ms)\n", fl / ms / 1e9, ms);
+    {
+      cx* mo;
+      CK(cudaMalloc(&mo, sizeof(cx) * 148 * 24 * 128 * 9));
+      auto run_mm = [&](auto kern, const char* name, int blocks) {
+        const int reps = 2000;
+        kern<<<blocks, 128>>>(U, mo, 10);
+        CK(cudaEventRecord(e0));
+        kern<<<blocks, 128>>>(U, mo, reps);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        // 4 products x 27 complex FMAs x 4 DFMA x 2 flop
+        printf("3x3 complex matmul code in registers, %s: %.2f TFLOP/s\n", name, 4.0 * 27 * 8 * reps * blocks * 128.0 / ms / 1e9);
+      };
+      run_mm(mm_peak<3>, "168-register budget, 12 warps/SM", 148 * 3 * 8);
+      run_mm(mm_peak<2>, "255-register budget, 8 warps/SM", 148 * 2 * 8);
+      run_mm(mm_peak<4>, "128-register budget, 16 warps/SM", 148 * 4 * 8);
+      CK(cudaFree(mo));
+    }
     lq_i64 n = (lq_i64)g.nchunk * 32 * 36;
     copy_k<<<148 * 16, 256>>>(U, U2, n);
     CK(cudaEventRecord(e0));
@@ -243,6 +287,8 @@ int main(int argc, char** argv) {
   V4F(128, 3, 8, -1);
   V4F(128, 3, 10, -1);
   V4F(128, 3, 4, -1);
+  V4F(128, 3, 34, -1);
+  V4F(128, 3, 32, -1);
 #define V5(BLOCK, MINB, PIPE)                                                                                      \
   vs.push_back({std::string("v5 pipelined block=" #BLOCK " minb=" #MINB " pipe=" #PIPE),                            \
                 [&] {                                                                                               \
@@ -303,6 +349,71 @@ int main(int argc, char** argv) {
     printf("%-52s %5d %4d %9.4f %9.1f %8.2f %10.2e %10.2e\n", v.name.c_str(), at.numRegs, occ * v.block / 32, ms,
            416.0 * nl / ms / 1e6, 3148.0 * nl / ms / 1e9, errE, errU);
     fflush(stdout);
+  }
+  // ---- checkerboard sweep sub-steps (8 launches = one sweep); every variant must reproduce the bits of PF = 0
+  {
+    cx* W;
+    CK(cudaMalloc(&W, ub));
+    std::vector<double> hW0(ub / 8), hW(ub / 8);
+    struct SV {
+      std::string name;
+      std::function<void(int, int)> run;
+      const void* func;
+      int block;
+    };
+    std::vector<SV> sv;
+#define SW(BLOCK, MINB, KIND, PF)                                                                                  \
+  sv.push_back({std::string(KIND == 0 ? "heatbath" : "overrelax") + " block=" #BLOCK " minb=" #MINB " pf=" #PF,    \
+                [&](int mu, int par) {                                                                              \
+                  lq_sweep4_kernel<BLOCK, MINB, KIND, PF><<<(unsigned)((g.vol / 2 + BLOCK - 1) / BLOCK), BLOCK>>>(  \
+                      g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);                                                    \
+                  CK(cudaGetLastError());                                                                           \
+                },                                                                                                  \
+                (const void*)lq_sweep4_kernel<BLOCK, MINB, KIND, PF>, BLOCK})
+    SW(128, 3, 0, 0);
+    SW(128, 3, 0, 1);
+    SW(128, 4, 0, 0);
+    SW(128, 5, 0, 0);
+    SW(128, 6, 0, 0);
+    SW(64, 8, 0, 0);
+    SW(64, 10, 0, 0);
+    SW(256, 2, 0, 0);
+    SW(128, 3, 1, 0);
+    SW(128, 4, 1, 0);
+    SW(128, 5, 1, 0);
+    SW(128, 6, 1, 0);
+    printf("%-52s %5s %4s %9s %9s %10s\n", "sweep variant (8 sub-steps)", "regs", "occ", "ms/sweep", "GB/s(alg)", "maxdiff");
+    for (size_t vi = 0; vi < sv.size(); ++vi) {
+      auto& v = sv[vi];
+      if (filter[0] && std::string("sweep").find(filter) == std::string::npos && v.name.find(filter) == std::string::npos) continue;
+      cudaFuncAttributes at;
+      CK(cudaFuncGetAttributes(&at, v.func));
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.func, v.block, 0));
+      CK(cudaMemcpy(W, U, ub, cudaMemcpyDeviceToDevice));
+      for (int mu = 0; mu < 4; ++mu)
+        for (int par = 0; par < 2; ++par) v.run(mu, par);
+      CK(cudaDeviceSynchronize());
+      const bool first_of_kind = v.name.find("minb=3 pf=0") != std::string::npos;
+      CK(cudaMemcpy((first_of_kind ? hW0 : hW).data(), W, ub, cudaMemcpyDeviceToHost));
+      double diff = 0;
+      if (!first_of_kind)
+        for (size_t i = 0; i < hW.size(); ++i) diff = fmax(diff, fabs(hW[i] - hW0[i]));
+      CK(cudaEventRecord(e0));
+      for (int r = 0; r < reps; ++r)
+        for (int mu = 0; mu < 4; ++mu)
+          for (int par = 0; par < 2; ++par) v.run(mu, par);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      ms /= reps;
+      // algorithmic bytes of a sweep: 8 sub-steps x (all links read once + 1/8 written) = 1296 B per link update
+      printf("%-52s %5d %4d %9.4f %9.1f %10.2e\n", v.name.c_str(), at.numRegs, occ * v.block / 32, ms,
+             1296.0 * nl / ms / 1e6, diff);
+      fflush(stdout);
+    }
+    CK(cudaFree(W));
   }
   return 0;
 }
