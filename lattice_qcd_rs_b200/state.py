@@ -30,7 +30,7 @@ import math
 
 import numpy as np
 
-from . import _capi
+from . import _capi, serde_io
 from ._capi import Context, LqError
 
 CA = 3.0  # LatticeState::CA, state.rs:796
@@ -81,6 +81,17 @@ class Rng:
     @classmethod
     def seed_from_u64(cls, seed):
         return cls(seed)
+
+    def checkpoint(self):
+        """The whole generator state (one u64): together with a serialized lattice state this resumes a run bit for
+        bit, because every device draw is a Philox stream keyed by the (seed, counter) pair drawn here."""
+        return self.state
+
+    @classmethod
+    def from_checkpoint(cls, state):
+        r = cls(0)
+        r.state = int(state) & 0xFFFFFFFFFFFFFFFF
+        return r
 
     def next_u64(self):
         self.state = (self.state + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
@@ -225,6 +236,33 @@ class LatticeStateDefault:
         st = type(self)(self._ctx.clone(), self._lattice)
         return st
 
+    # -- serde (feature `serde-serialize`, state.rs:654): what serde_json / bincode 1.x write for this struct; the
+    #    links travel device -> host AoS -> bytes, the layouts are documented in serde_io.py
+    def to_json(self):
+        lat = self._lattice
+        return serde_io.dumps_json(serde_io.state_to_json_obj(lat.size(), lat.dim(), lat.D, self.beta(), self.link_matrix()))
+
+    def to_bincode(self, seq_prefix=True):
+        lat = self._lattice
+        return serde_io.state_to_bincode(lat.size(), lat.dim(), lat.D, self.beta(), self.link_matrix(), seq_prefix)
+
+    @classmethod
+    def _from_plain(cls, d, device, lib):
+        try:
+            lattice = LatticeCyclic(d["size"], d["dim"], d["D"])
+        except LatticeInitializationError as e:
+            raise StateInitializationError("LatticeInitializationError", str(e))
+        return cls.new(lattice, d["beta"], d["links"], device=device, lib=lib)
+
+    @classmethod
+    def from_json(cls, text, D=4, device=0, lib=None):
+        import json
+        return cls._from_plain(serde_io.state_from_json_obj(json.loads(text), D), device, lib)
+
+    @classmethod
+    def from_bincode(cls, buf, D=4, device=0, lib=None, seq_prefix=True):
+        return cls._from_plain(serde_io.state_from_bincode(buf, D, seq_prefix), device, lib)
+
     # -- device handle for the method classes
     def _touch(self):
         self._host_links = None
@@ -327,6 +365,34 @@ class LatticeStateEFSyncDefault(LatticeStateDefault):
         st = LatticeStateDefault(self._ctx, self._lattice)
         self._ctx = None
         return st
+
+    # -- serde (state.rs:1047-1062: e_field, t, lattice_state)
+    def to_json(self):
+        lat = self._lattice
+        return serde_io.dumps_json(serde_io.ef_state_to_json_obj(lat.size(), lat.dim(), lat.D, self.beta(),
+                                                                 self.link_matrix(), self.e_field(), self.t()))
+
+    def to_bincode(self, seq_prefix=True):
+        lat = self._lattice
+        return serde_io.ef_state_to_bincode(lat.size(), lat.dim(), lat.D, self.beta(), self.link_matrix(),
+                                            self.e_field(), self.t(), seq_prefix)
+
+    @classmethod
+    def _from_plain(cls, d, device, lib):
+        try:
+            lattice = LatticeCyclic(d["size"], d["dim"], d["D"])
+        except LatticeInitializationError as e:
+            raise StateInitializationError("LatticeInitializationError", str(e))
+        return cls.new(lattice, d["beta"], d["e_field"], d["links"], d["t"], device=device, lib=lib)
+
+    @classmethod
+    def from_json(cls, text, D=4, device=0, lib=None):
+        import json
+        return cls._from_plain(serde_io.ef_state_from_json_obj(json.loads(text), D), device, lib)
+
+    @classmethod
+    def from_bincode(cls, buf, D=4, device=0, lib=None, seq_prefix=True):
+        return cls._from_plain(serde_io.ef_state_from_bincode(buf, D, seq_prefix), device, lib)
 
     def _touch(self):
         self._host_e = None
