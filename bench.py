@@ -14,7 +14,7 @@ value : device-resident (links stay in HBM between trajectories), CUDA events on
 e2e   : the same trajectory through the C ABI with HOST buffers: links uploaded from pinned host memory before and
         downloaded after every trajectory, inside the timed region.
 --impl reference : the CPU restatement of the reference loops (oracle/, OpenMP over all host cores; the Rust crate
-        cannot be built in this image) on a bounded sample (8^4, the config the reference runs on a CPU today).
+        cannot be built in this image) on a bounded sample of the same 32^4 workload (see CpuSample).
 """
 import argparse
 import json
@@ -99,52 +99,63 @@ class ClockSampler:
         return out
 
 
-def cpu_sample(target_s=10.0, ext=8):
-    """Oracle (C++/OpenMP restatement of the reference loops, literal mode) timed on the host cores: full HMC
-    trajectories (same beta, dt, MD steps) on a bounded ext^4 sample."""
-    from oracle.oracle import Oracle
-    o = Oracle(4, ext, a=SPACING, beta=BETA)
-    o.set_num_threads(os.cpu_count() or 1)
-    U = o.links_random(SEED)
-    reps, t0 = 0, time.perf_counter()
-    while True:
-        r = o.hmc_trajectory(U, DT, MD_STEPS, SEED, reps, literal=True)
-        U = o.normalize_links(r["U"])
-        reps += 1
-        el = time.perf_counter() - t0
-        if el >= target_s or reps >= 50:
-            break
-    return dict(value=MD_STEPS * o.nl * reps / el, unit="link-updates/s", cores=o.num_threads(), kind="port",
-                sample=f"{reps} full HMC trajectories ({MD_STEPS} MD steps, dt={DT}, Gauss projection, literal reference "
-                       f"loops incl. 28-matmul derivative_e) on a {ext}^4 lattice, g++ -O3 -fopenmp, {el:.1f} s; "
-                       "C++ restatement of lattice-qcd-rs v0.2.1, not the Rust binary"), reps, el
+# The CPU arm runs a BOUNDED SAMPLE of the same 32^4 workload: a full trajectory costs minutes on the host cores, so a
+# sample step is 1/25 of one -- SAMPLE_MD symplectic steps and SAMPLE_GAUSS Gauss-projection iterations (the 100 : 173
+# mix of the GPU trajectory on this start configuration) on the full 32^4 hot lattice, literal reference loops.  What a
+# sample leaves out (momentum refresh, 2 x H_total, accept, normalise) is < 1 % of a trajectory on either side.
+SAMPLE_MD, SAMPLE_GAUSS = 4, 7
+
+
+class CpuSample:
+    def __init__(self, ext):
+        from oracle.oracle import Oracle
+        self.o = o = Oracle(4, ext, a=SPACING, beta=BETA)
+        o.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; this arm uses every host core
+        self.U = o.links_random(SEED)
+        self.E = o.momenta_refresh(SEED, 1)
+        self.ext = ext
+
+    def step(self):
+        o = self.o
+        for _ in range(SAMPLE_GAUSS):
+            self.E = o.project_to_gauss_step(self.U, self.E)
+        self.U, self.E = o.integrate(self.U, self.E, "symplectic", DT, n=SAMPLE_MD, literal=True)
+
+    def describe(self):
+        return (f"each step = {SAMPLE_MD} symplectic-Euler MD steps (dt={DT}) + {SAMPLE_GAUSS} Gauss-projection iterations "
+                f"on the full {self.ext}^4 beta={BETA} hot lattice (1/25 of the GPU trajectory's 100 : 173 mix; momentum "
+                "refresh, 2x H_total, accept and normalise left out: < 1 % of a trajectory), literal reference loops incl. "
+                "the 28-matmul derivative_e, g++ -O3 -fopenmp on all host cores; C++ restatement of lattice-qcd-rs "
+                "v0.2.1 (oracle/), not the Rust binary")
+
+
+def cpu_sample(ext, steps=1, warmup=0):
+    """Oracle (C++/OpenMP restatement of the reference loops, literal mode) timed on the host cores."""
+    cs = CpuSample(ext)
+    for _ in range(warmup):
+        cs.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cs.step()
+    el = time.perf_counter() - t0
+    val = SAMPLE_MD * cs.o.nl * steps / el
+    return dict(value=val, unit="link-updates/s", cores=cs.o.num_threads(), kind="port",
+                sample=cs.describe() + f"; {steps} step(s), {el:.1f} s"), el
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.oracle import Oracle
-    ext = 8
-    o = Oracle(4, ext, a=SPACING, beta=BETA)
-    o.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core
-    U = o.links_random(SEED)
-    for k in range(args.warmup):
-        U = o.normalize_links(o.hmc_trajectory(U, DT, MD_STEPS, SEED, k, literal=True)["U"])
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        U = o.normalize_links(o.hmc_trajectory(U, DT, MD_STEPS, SEED, 1000 + k, literal=True)["U"])
-    el = time.perf_counter() - t0
-    val = MD_STEPS * o.nl * args.steps / el
-    sample = (f"each step = 1 full HMC trajectory ({MD_STEPS} MD steps, dt={DT}) on a bounded {ext}^4 sample of the "
-              "workload; C++/OpenMP restatement of the reference loops (literal), not the Rust binary")
+    cpu, el = cpu_sample(args.extent, steps=args.steps, warmup=args.warmup)
+    val = cpu["value"]
     line = {
         "impl": "reference", "metric": "HMC link-updates/sec at 32^4 f64", "value": val, "unit": "link-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "32^4 beta=6.0 HMC (100 MD steps/trajectory), hot start", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "link-updates/s", "cores": o.num_threads(), "kind": "port",
-                         "sample": sample},
+        "config": {"workload": f"{args.extent}^4 beta={BETA} HMC (100 MD steps/trajectory), hot start",
+                   "sample": cpu["sample"]},
+        "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": "link-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -286,7 +297,7 @@ def run_ours(args):
             tj = json.load(f)
         if tj.get("extent") == L:
             traffic = tj.get("dram_bytes_per_launch")
-    cpu = cpu_sample()[0] if world == 1 else None  # reported on rank 0 at N = 1 only
+    cpu = cpu_sample(L, steps=1, warmup=0)[0] if world == 1 else None  # reported on rank 0 at N = 1 only
     ns_local = nl_local // 4
 
     def _roof(kernel, bytes_per_launch, n, ms_tot):

@@ -272,10 +272,7 @@ static int launch(lq_ctx* c, lq_i64 n, const F& f) {
   LQ_CHECK(cudaGetLastError());
   return LQ_OK;
 }
-template <class F>
-static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
-  constexpr int K = F::K;
-  lq_i64 nb = (n + LQ_RBLOCK - 1) / LQ_RBLOCK;
+static int reduce_reserve(lq_ctx* c, lq_i64 nb, int K) {
   if ((size_t)(nb * K) > c->partial_cap) {
     rt_free(c->d_partial);
     c->d_partial = nullptr;
@@ -283,7 +280,12 @@ static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
     if (rc) return rc;
     c->partial_cap = (size_t)nb * K;
   }
-  lq_reduce_k<F><<<(unsigned)nb, LQ_RBLOCK, 0, c->stream>>>(f, n, c->d_partial);
+  return LQ_OK;
+}
+// second stage of every reduction: fixed-order sum of the nb per-block partials, optional device-side all-reduce,
+// one host synchronisation; result in c->h_result[0..K)
+template <int K>
+static int reduce_finish(lq_ctx* c, lq_i64 nb) {
   lq_final_k<K><<<1, LQ_RBLOCK, 0, c->stream>>>(c->d_partial, nb, c->d_result);
   c->launches += 2;
   LQ_CHECK(cudaGetLastError());
@@ -308,6 +310,15 @@ static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
     if (err) return LQ_E_COMM;
   }
   return LQ_OK;
+}
+template <class F>
+static int reduce(lq_ctx* c, lq_i64 n, const F& f) {
+  constexpr int K = F::K;
+  lq_i64 nb = (n + LQ_RBLOCK - 1) / LQ_RBLOCK;
+  int rc = reduce_reserve(c, nb, K);
+  if (rc) return rc;
+  lq_reduce_k<F><<<(unsigned)nb, LQ_RBLOCK, 0, c->stream>>>(f, n, c->d_partial);
+  return reduce_finish<K>(c, nb);
 }
 #endif
 
@@ -696,6 +707,14 @@ int lq_links_set_random(lq_ctx* c, uint64_t seed, uint64_t counter) {
 static int plaquette_all(lq_ctx* c, double v[3]) {
   LQ_TRY(ensure_halo(c, 0));
   ProfScope ps(c, LQ_PROF_PLAQUETTE);
+#if defined(LQ_HAVE_TUNED) && !defined(LQ_HOST_EMU)
+  if (lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+    const lq_i64 nb = lq_tuned_plaquette_blocks(c->g);
+    LQ_TRY(reduce_reserve(c, nb, 3));
+    LQ_CHECK(lq_tuned_plaquette(c->stream, c->g, c->U, c->CA, c->d_partial));
+    LQ_TRY(reduce_finish<3>(c, nb));
+  } else
+#endif
   LQ_DISPATCH(c, LQ_TRY((reduce(c, KPlaquette<DD>::items(c->g), KPlaquette<DD>{c->g, c->U, c->CA}))));
   for (int k = 0; k < 3; ++k) v[k] = c->h_result[k];
   return global_sum(c, v, 3);

@@ -412,6 +412,10 @@ def test_tuned_kernels_equal_generic_kernels(backend, ext):
         c.set_flags(flags)
         c.links_upload(U)
         c.efield_upload(E)
+        # plaquette reduction (tuned: lq_plaq4_kernel): same terms, another summation order
+        pq, hl = c.average_trace_plaquette(), c.hamiltonian_links()
+        assert abs(pq - o.average_trace_plaquette(U)) <= RTOL * abs(pq)
+        assert abs(hl - o.hamiltonian_links(U)) <= RTOL * abs(hl)
         c.symplectic_n(0.01, 3)
         md = (c.links_download(), c.efield_download())
         assert rel(md[0], Uo) <= RTOL and rel(md[1], Eo) <= RTOL
@@ -423,6 +427,7 @@ def test_tuned_kernels_equal_generic_kernels(backend, ext):
         c.sweep_overrelax(1)
         orx = c.links_download()
         assert rel(orx, Uor) <= 1e-9
-        res.append((md, hb, orx))
+        res.append((md, hb, orx, pq, hl))
     assert rel(res[0][0][0], res[1][0][0]) <= 1e-14 and rel(res[0][0][1], res[1][0][1]) <= 1e-14
     assert rel(res[0][1], res[1][1]) <= 1e-12 and rel(res[0][2], res[1][2]) <= 1e-12
+    assert abs(res[0][3] - res[1][3]) <= 1e-14 * abs(res[1][3]) and abs(res[0][4] - res[1][4]) <= 1e-13 * abs(res[1][4])
