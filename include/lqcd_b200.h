@@ -129,6 +129,15 @@ int lq_symplectic_n(lq_ctx*, double dt, int64_t n_steps);
 /* simulate_using_leapfrog_n, state.rs:321-358: sync_leap, (n-1) x leap_leap, leap_sync */
 int lq_leapfrog_n(lq_ctx*, double dt, int64_t n_steps);
 int lq_reunitarize(lq_ctx*);                       /* normalize_link_matrices, state.rs:754-756; su3.rs:279-303 */
+/* Integrator options beyond the crate's: compositions of the same two updates -- integrate_efield
+ * (integrator/mod.rs:240-254) and integrate_link (:216-233) or its exponential form (use_exp: U <- exp(i dt E) U,
+ * su3.rs:832-855, keeps the links in SU(3) and makes the step time-reversible).  The selection is what lq_md_n and
+ * lq_hmc_trajectory run; (LQ_INTEGRATOR_SYMPLECTIC_EULER, -, 0) -- the default -- is lq_symplectic_n, the reference's
+ * SymplecticEulerRayon::integrate_symplectic.  LQ_INTEGRATOR_OMELYAN: E(l dt) U(dt/2) E((1-2l) dt) U(dt/2) E(l dt),
+ * 0 < l < 1/2 (second-order minimum norm: l = 0.1931833275037836). */
+enum { LQ_INTEGRATOR_SYMPLECTIC_EULER = 0, LQ_INTEGRATOR_OMELYAN = 1 };
+int lq_set_integrator(lq_ctx*, int kind, double lambda, int use_exp);
+int lq_md_n(lq_ctx*, double dt, int64_t n_steps);  /* n steps of the selected integrator, t += n */
 
 /* ---- momenta + Gauss law ----------------------------------------------------------------------------------- */
 /* EField::new_determinist with Normal(0, sigma) (field.rs:1086-1099; state.rs:1097 sigma = 0.5/beta) */

@@ -25,6 +25,8 @@ ERRORS = {
 SYNC_SYNC, LEAP_LEAP, SYNC_LEAP, LEAP_SYNC, SYMPLECTIC = range(5)
 OR_ROTATION, OR_REVERSE = 0, 1
 FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED, FLAG_GENERIC_KERNELS = 1, 2, 4, 8
+INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_OMELYAN = 0, 1
+OMELYAN_LAMBDA = 0.1931833275037836  # second-order minimum-norm coefficient (Omelyan, Mryglod, Folk 2003)
 
 HALO_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, C.c_int)
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, _vp, _dp, C.c_int)
@@ -90,6 +92,8 @@ SYMBOLS = {
     "lq_integrate": (C.c_int, [_vp, C.c_int, C.c_double]),
     "lq_symplectic_n": (C.c_int, [_vp, C.c_double, C.c_int64]),
     "lq_leapfrog_n": (C.c_int, [_vp, C.c_double, C.c_int64]),
+    "lq_set_integrator": (C.c_int, [_vp, C.c_int, C.c_double, C.c_int]),
+    "lq_md_n": (C.c_int, [_vp, C.c_double, C.c_int64]),
     "lq_reunitarize": (C.c_int, [_vp]),
     "lq_momenta_refresh": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_double]),
     "lq_gauss_field": (C.c_int, [_vp, _dp, C.c_int64]),
@@ -388,6 +392,13 @@ class Context:
 
     def leapfrog_n(self, dt, n):
         self._check(self.lib.lq_leapfrog_n(self._h, dt, int(n)), "lq_leapfrog_n")
+
+    def set_integrator(self, kind=INTEGRATOR_SYMPLECTIC_EULER, lam=OMELYAN_LAMBDA, use_exp=False):
+        """What md_n / hmc_trajectory integrate with; the default (0, -, False) is the reference's symplectic Euler."""
+        self._check(self.lib.lq_set_integrator(self._h, int(kind), float(lam), int(use_exp)), "lq_set_integrator")
+
+    def md_n(self, dt, n):
+        self._check(self.lib.lq_md_n(self._h, dt, int(n)), "lq_md_n")
 
     def reunitarize(self):
         self._check(self.lib.lq_reunitarize(self._h), "lq_reunitarize")

@@ -98,6 +98,8 @@ struct lq_ctx {
   LqGeom g;
   double a, beta, CA;
   int flags;
+  int integ_kind, integ_exp;  // lq_set_integrator: what lq_md_n / lq_hmc_trajectory run (0, 0 = the reference's)
+  double integ_lambda;
   int64_t t;
   int64_t launches;
   bool decomposed;
@@ -484,6 +486,9 @@ int lq_ctx_clone(const lq_ctx* src, lq_ctx** out) {
   LQ_TRY(ctx_create_common(&c, src->device, src->g.D, gext, src->nproc, coord, src->a, src->beta, src->CA));
   LQ_GUARD(c);
   c->flags = src->flags;
+  c->integ_kind = src->integ_kind;
+  c->integ_exp = src->integ_exp;
+  c->integ_lambda = src->integ_lambda;
   c->t = src->t;
   c->comm = src->comm;
   c->has_comm = src->has_comm;
@@ -954,6 +959,45 @@ int lq_symplectic_n(lq_ctx* c, double dt, int64_t n) {
   c->t += n;
   return LQ_OK;
 }
+// Integrator options beyond the reference's (not parity paths of the crate, checked against the
+// oracle's composition of the same E / U steps).  All are compositions of the two reference updates, integrate_efield
+// (integrator/mod.rs:240-254) and integrate_link (:216-233, Euler) or its exponential form (use_exp, su3.rs:832-855):
+//   symplectic Euler / leap-frog   E(dt/2) U(dt) E(dt/2)                                   (symplectic_euler_rayon.rs:220-252)
+//   Omelyan 2nd-order minimum norm E(l dt) U(dt/2) E((1-2l) dt) U(dt/2) E(l dt),  l = 0.1931833...
+// with the adjacent E kicks of consecutive steps merged.  (0, any, 0) is lq_symplectic_n itself (fused kernels).
+int lq_set_integrator(lq_ctx* c, int kind, double lambda, int use_exp) {
+  if (!c || (kind != LQ_INTEGRATOR_SYMPLECTIC_EULER && kind != LQ_INTEGRATOR_OMELYAN)) return LQ_E_BADARG;
+  if (kind == LQ_INTEGRATOR_OMELYAN && !(lambda > 0.0 && lambda < 0.5)) return LQ_E_BADARG;
+  c->integ_kind = kind;
+  c->integ_lambda = lambda;
+  c->integ_exp = use_exp != 0;
+  return LQ_OK;
+}
+int lq_md_n(lq_ctx* c, double dt, int64_t n) {
+  if (!c) return LQ_E_BADARG;
+  if (n <= 0) return LQ_E_ZERO_STEPS;
+  LQ_GUARD(c);
+  if (c->integ_kind == LQ_INTEGRATOR_SYMPLECTIC_EULER && !c->integ_exp) return lq_symplectic_n(c, dt, n);
+  const int ex = c->integ_exp;
+  if (c->integ_kind == LQ_INTEGRATOR_SYMPLECTIC_EULER) {
+    LQ_TRY(efield_step(c, dt / 2.0, 1));
+    for (int64_t k = 0; k < n; ++k) {
+      LQ_TRY(link_step(c, c->U, c->U, dt, ex));
+      LQ_TRY(efield_step(c, k + 1 < n ? dt : dt / 2.0, 1));
+    }
+  } else {
+    const double l = c->integ_lambda;
+    LQ_TRY(efield_step(c, l * dt, 1));
+    for (int64_t k = 0; k < n; ++k) {
+      LQ_TRY(link_step(c, c->U, c->U, dt / 2.0, ex));
+      LQ_TRY(efield_step(c, (1.0 - 2.0 * l) * dt, 1));
+      LQ_TRY(link_step(c, c->U, c->U, dt / 2.0, ex));
+      LQ_TRY(efield_step(c, k + 1 < n ? 2.0 * l * dt : l * dt, 1));
+    }
+  }
+  c->t += n;
+  return LQ_OK;
+}
 int lq_leapfrog_n(lq_ctx* c, double dt, int64_t n) {
   if (!c) return LQ_E_BADARG;
   if (n <= 0) return LQ_E_ZERO_STEPS;
@@ -1204,7 +1248,7 @@ int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint
   int64_t t0 = c->t;
   double h0, h1;
   LQ_TRY(lq_hamiltonian_total(c, &h0));
-  LQ_TRY(lq_symplectic_n(c, dt, n_steps));  // hybrid_monte_carlo.rs:573-582
+  LQ_TRY(lq_md_n(c, dt, n_steps));  // hybrid_monte_carlo.rs:573-582 (lq_symplectic_n unless lq_set_integrator chose otherwise)
   LQ_TRY(lq_hamiltonian_total(c, &h1));
   double p = fmax(fmin(exp(h0 - h1), 1.0), 0.0);  // :584-589
   LqStream acc(seed, counter, 0xFFFFFFFFFEull);

@@ -414,7 +414,13 @@ class LatticeStateEFSyncDefault(LatticeStateDefault):
             raise MultiIntegrationError("ZeroIntegration")
         if isinstance(integrator, SymplecticEulerCuda):
             new = self.clone()
-            new._touch().symplectic_n(delta_t, numbers_of_times)
+            try:
+                ctx = new._touch()
+                integrator._select(ctx)  # the reference's symplectic Euler (lq_symplectic_n) unless it is OmelyanCuda
+                ctx.md_n(delta_t, numbers_of_times)
+                SymplecticEulerCuda._select(integrator, ctx)
+            except LqError as e:
+                raise _wrap(e)
             return new
         return _n_times(self, numbers_of_times, lambda s: integrator.integrate_symplectic(s, delta_t))
 
@@ -523,6 +529,40 @@ class SymplecticEulerCuda:
     def integrate_symplectic(self, l, delta_t):
         return self._step(l, _capi.SYMPLECTIC, delta_t)
 
+    def _select(self, ctx):
+        ctx.set_integrator(_capi.INTEGRATOR_SYMPLECTIC_EULER, _capi.OMELYAN_LAMBDA, False)
+
+
+class OmelyanCuda(SymplecticEulerCuda):
+    """An integrator the crate does not have, offered through the same SymplecticIntegrator
+    surface: `integrate_symplectic` is one second-order minimum-norm step
+        E(l dt) U(dt/2) E((1-2l) dt) U(dt/2) E(l dt),   l = 0.1931833275037836,
+    built from the reference's own two updates (integrate_efield, integrator/mod.rs:240-254; integrate_link,
+    :216-233), with `use_exp` replacing the Euler link update by U <- exp(i dt E) U (su3.rs:832-855: links stay in
+    SU(3), the step is time-reversible).  The leap-frog half-step compositions are inherited unchanged.  Passing it to
+    HybridMonteCarlo(Diagnostic) makes the trajectory use it."""
+
+    def __init__(self, lam=_capi.OMELYAN_LAMBDA, use_exp=True):
+        self.lam, self.use_exp = float(lam), bool(use_exp)
+
+    @classmethod
+    def new(cls, lam=_capi.OMELYAN_LAMBDA, use_exp=True):
+        return cls(lam, use_exp)
+
+    def _select(self, ctx):
+        ctx.set_integrator(_capi.INTEGRATOR_OMELYAN, self.lam, self.use_exp)
+
+    def integrate_symplectic(self, l, delta_t):
+        new = l.clone()
+        try:
+            ctx = new._touch()
+            self._select(ctx)
+            ctx.md_n(delta_t, 1)
+            SymplecticEulerCuda._select(self, ctx)
+        except LqError as e:
+            raise _wrap(e)
+        return new
+
 
 # ------------------------------------------------------------------------------------------------ Monte-Carlo methods
 class MonteCarlo:
@@ -574,7 +614,11 @@ class HybridMonteCarloDiagnostic(MonteCarlo):
             raise MultiIntegrationError("ZeroIntegration")
         seed, counter = _draw(self._rng)
         try:
-            r = state._touch().hmc_trajectory(self._dt, self._n, seed, counter, sigma=0.5 / state.beta())
+            ctx = state._touch()
+            select = getattr(self._integrator, "_select", None)
+            if select is not None:
+                select(ctx)  # SymplecticEulerCuda: the reference's integrator; OmelyanCuda: the option
+            r = ctx.hmc_trajectory(self._dt, self._n, seed, counter, sigma=0.5 / state.beta())
         except LqError as e:
             raise _wrap(e)
         self._prob_replace_last, self._has_replace_last = r["prob"], r["accepted"]

@@ -250,6 +250,26 @@ class Oracle:
                              C.c_int(int(literal)))
         return U, E
 
+    def md_n(self, U, E, dt, n, kind=0, lam=0.1931833275037836, use_exp=False, literal=True):
+        """Integrator options beyond the crate's, composed from the two reference updates
+        integrate_efield (integrator/mod.rs:240-254) and integrate_link (:216-233) / its exponential form:
+        kind 0: E(dt/2) U(dt) E(dt/2) per step; kind 1 (Omelyan): E(l dt) U(dt/2) E((1-2l) dt) U(dt/2) E(l dt);
+        adjacent E kicks of consecutive steps merged (one kick of the summed length, as the library does)."""
+        ustep = self.link_step_exp if use_exp else self.link_step
+        if kind == 0:
+            E = self.efield_step(U, E, dt / 2.0, literal)
+            for k in range(n):
+                U = ustep(U, E, dt)
+                E = self.efield_step(U, E, dt if k + 1 < n else dt / 2.0, literal)
+        else:
+            E = self.efield_step(U, E, lam * dt, literal)
+            for k in range(n):
+                U = ustep(U, E, dt / 2.0)
+                E = self.efield_step(U, E, (1.0 - 2.0 * lam) * dt, literal)
+                U = ustep(U, E, dt / 2.0)
+                E = self.efield_step(U, E, 2.0 * lam * dt if k + 1 < n else lam * dt, literal)
+        return U, E
+
     def leapfrog_n(self, U, E, dt, n, literal=True):
         U, E = U.copy(), E.copy()
         self.L.lqo_leapfrog_n(*self._g(), _p(U), _p(E), C.c_double(dt), C.c_int64(n), C.c_double(self.CA),

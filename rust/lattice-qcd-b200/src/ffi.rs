@@ -57,6 +57,9 @@ extern "C" {
     pub fn lq_integrate(c: *mut lq_ctx, kind: c_int, dt: c_double) -> c_int;
     /// simulate_symplectic_n (state.rs:470-492)
     pub fn lq_symplectic_n(c: *mut lq_ctx, dt: c_double, n: i64) -> c_int;
+    /// integrator options beyond the crate's (Omelyan, exponential link update): what lq_md_n / lq_hmc_trajectory run
+    pub fn lq_set_integrator(c: *mut lq_ctx, kind: c_int, lambda: c_double, use_exp: c_int) -> c_int;
+    pub fn lq_md_n(c: *mut lq_ctx, dt: c_double, n: i64) -> c_int;
     /// normalize_link_matrices (state.rs:754-756)
     pub fn lq_reunitarize(c: *mut lq_ctx) -> c_int;
     /// EField::new_determinist + project_to_gauss (field.rs:1086-1099, 1265-1294)

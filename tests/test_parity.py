@@ -431,3 +431,54 @@ def test_tuned_kernels_equal_generic_kernels(backend, ext):
     assert rel(res[0][0][0], res[1][0][0]) <= 1e-14 and rel(res[0][0][1], res[1][0][1]) <= 1e-14
     assert rel(res[0][1], res[1][1]) <= 1e-12 and rel(res[0][2], res[1][2]) <= 1e-12
     assert abs(res[0][3] - res[1][3]) <= 1e-14 * abs(res[1][3]) and abs(res[0][4] - res[1][4]) <= 1e-13 * abs(res[1][4])
+
+
+@pytest.mark.parametrize("D,ext", [(4, [4, 4, 4, 4]), (3, [4, 6, 4])])
+def test_integrator_options(backend, D, ext):
+    """Integrators beyond the crate's (lq_set_integrator / lq_md_n): compositions of the reference's own
+    E and U updates.  Parity against the oracle's composition of the same steps; with the exponential link update the
+    links stay in SU(3) and the map is time-reversible; Omelyan's energy error beats leap-frog's at equal step."""
+    from lattice_qcd_rs_b200 import INTEGRATOR_OMELYAN, INTEGRATOR_SYMPLECTIC_EULER, OMELYAN_LAMBDA
+    o = Oracle(D, ext, a=1.0, beta=6.0)
+    c = backend(D, ext, a=1.0, beta=6.0)
+    U = hot(o)
+    E = o.momenta_refresh(SEED_RNG, 21)
+    h0 = o.hamiltonian_total(U, E)
+    dh = {}
+    for kind, use_exp in ((INTEGRATOR_SYMPLECTIC_EULER, False), (INTEGRATOR_SYMPLECTIC_EULER, True),
+                          (INTEGRATOR_OMELYAN, False), (INTEGRATOR_OMELYAN, True)):
+        c.links_upload(U)
+        c.efield_upload(E)
+        c.set_t(0)
+        c.set_integrator(kind, OMELYAN_LAMBDA, use_exp)
+        c.md_n(0.02, 5)
+        Uo, Eo = o.md_n(U, E, 0.02, 5, kind=kind, lam=OMELYAN_LAMBDA, use_exp=use_exp)
+        Ug, Eg = c.links_download(), c.efield_download()
+        assert c.t == 5
+        assert rel(Ug, Uo) <= RTOL and rel(Eg, Eo) <= RTOL
+        dh[(kind, use_exp)] = abs(c.hamiltonian_total() - h0)
+        if use_exp:
+            # unitarity is kept to rounding (the Euler update drifts at O(dt^2) per step) ...
+            M = Ug.reshape(-1, 3, 3, 2)
+            M = (M[..., 0] + 1j * M[..., 1]).transpose(0, 2, 1)  # column-major AoS -> row-major matrices
+            assert np.abs(M @ M.conj().transpose(0, 2, 1) - np.eye(3)).max() <= 1e-13
+            # ... and the step is reversible: flip the momenta, integrate back, recover the start
+            c.efield_upload(-Eg)
+            c.md_n(0.02, 5)
+            assert rel(c.links_download(), U) <= 1e-11 and rel(-c.efield_download(), E) <= 1e-11
+    assert dh[(INTEGRATOR_OMELYAN, True)] < 0.5 * dh[(INTEGRATOR_SYMPLECTIC_EULER, True)]
+    # the default selection is the reference's integrator: lq_md_n == lq_symplectic_n
+    c.set_integrator(INTEGRATOR_SYMPLECTIC_EULER, OMELYAN_LAMBDA, False)
+    c.links_upload(U)
+    c.efield_upload(E)
+    c.md_n(0.01, 3)
+    a = (c.links_download(), c.efield_download())
+    c.links_upload(U)
+    c.efield_upload(E)
+    c.symplectic_n(0.01, 3)
+    assert np.array_equal(a[0], c.links_download()) and np.array_equal(a[1], c.efield_download())
+    from lattice_qcd_rs_b200 import LqError
+    with pytest.raises(LqError):
+        c.set_integrator(INTEGRATOR_OMELYAN, 0.7, True)
+    with pytest.raises(LqError):
+        c.set_integrator(5, 0.2, True)

@@ -158,3 +158,34 @@ def test_sweeps_through_monte_carlo_trait(lib):
     state = state.monte_carlo_step(combo)
     state.normalize_link_matrices()
     assert np.isfinite(state.hamiltonian_links())
+
+
+def test_omelyan_integrator_through_the_trait_surface(lib):
+    """OmelyanCuda (an option the crate does not have) plugs into the same places as the reference's
+    integrators: simulate_symplectic(_n) and HybridMonteCarloDiagnostic::new(delta_t, n, integrator, rng)."""
+    rng = lq.Rng(SEED_RNG)
+    st = lq.LatticeStateEFSyncDefault.new_determinist(1.0, 6.0, 4, rng, lib=lib)
+    h0 = st.hamiltonian_total()
+    euler = st.simulate_symplectic_n(lq.SymplecticEulerCuda.new(), 0.02, 10)
+    omel = st.simulate_symplectic_n(lq.OmelyanCuda.new(), 0.02, 10)
+    one_by_one = st
+    for _ in range(2):
+        one_by_one = one_by_one.simulate_symplectic(lq.OmelyanCuda.new(), 0.02)
+    two = st.simulate_symplectic_n(lq.OmelyanCuda.new(), 0.02, 2)
+    assert one_by_one.t() == two.t() == 2
+    # n merged steps == n single steps up to the rounding of the merged kick (2 l dt vs l dt + l dt)
+    assert np.abs(one_by_one.link_matrix() - two.link_matrix()).max() <= 1e-13
+    assert omel.t() == euler.t() == 10
+    assert abs(omel.hamiltonian_total() - h0) < 0.2 * abs(euler.hamiltonian_total() - h0)
+    # st itself is untouched (integrators return new states) and still integrates with the reference's rule
+    again = st.simulate_symplectic_n(lq.SymplecticEulerCuda.new(), 0.02, 10)
+    assert np.array_equal(again.link_matrix(), euler.link_matrix())
+    plain = lq.LatticeStateDefault.new(st.lattice(), 6.0, st.link_matrix(), lib=lib)
+    hmc = lq.HybridMonteCarloDiagnostic(0.02, 10, lq.OmelyanCuda.new(), lq.Rng(5))
+    plain = plain.monte_carlo_step(hmc)
+    p_om = hmc.prob_replace_last()
+    plain2 = lq.LatticeStateDefault.new(st.lattice(), 6.0, st.link_matrix(), lib=lib)
+    hmc2 = lq.HybridMonteCarloDiagnostic(0.02, 10, lq.SymplecticEulerCuda.new(), lq.Rng(5))
+    plain2 = plain2.monte_carlo_step(hmc2)
+    assert 0.0 <= hmc2.prob_replace_last() <= 1.0 and 0.0 <= p_om <= 1.0
+    assert p_om >= hmc2.prob_replace_last() - 1e-12  # same momenta (same seed), smaller energy error
