@@ -601,6 +601,12 @@ int lq_is_decomposed(const lq_ctx* c, int dir) { return (c && dir >= 0 && dir < 
 
 // ---------------------------------------------------------------------------------------------- marshalling
 static int links_from_device_aos(lq_ctx* c, const double* d_aos) {
+#if defined(LQ_HAVE_TUNED) && !defined(LQ_HOST_EMU)
+  if (lq_tuned_aos_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+    LQ_CHECK(lq_tuned_links_aos(c->stream, c->g, c->U, const_cast<double*>(d_aos), false));
+    c->launches++;
+  } else
+#endif
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinksFromAos<DD>{c->g, d_aos, c->U}))));
   c->halo_ok[0] = false;
   c->g_valid = false;
@@ -613,6 +619,13 @@ static int efield_from_device_aos(lq_ctx* c, const double* d_aos) {
   return LQ_OK;
 }
 static int links_to_device_aos(lq_ctx* c, double* d_aos) {
+#if defined(LQ_HAVE_TUNED) && !defined(LQ_HOST_EMU)
+  if (lq_tuned_aos_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+    LQ_CHECK(lq_tuned_links_aos(c->stream, c->g, c->U, d_aos, true));
+    c->launches++;
+    return LQ_OK;
+  }
+#endif
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KLinksToAos<DD>{c->g, c->U, d_aos}))));
   return LQ_OK;
 }

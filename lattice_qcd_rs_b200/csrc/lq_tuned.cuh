@@ -609,6 +609,88 @@ __global__ void __launch_bounds__(192, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// AoS <-> chunked-SoA transposition of the links at the C-ABI boundary (lq_links_upload / lq_links_download:
+// LatticeStateNew::new, set_link_matrix, link_matrix(), state.rs:779-815), D = 4, ext0 a multiple of 32.
+// A row of x0 is one contiguous run on BOTH sides: ext0/32 whole chunks of the device layout (ext0 x 576 B) and ext0
+// sites x 4 links x 144 B of the reference's Vec<Matrix3<Complex<f64>>>.  One block per row: a single thread moves the
+// row into shared memory with ONE bulk asynchronous copy (TMA, cp.async.bulk + mbarrier transaction count), the block
+// permutes it in shared memory (slot -> x0: even sites first; plane-major -> link-major; row-major 3x3 -> nalgebra's
+// column-major), and one bulk copy writes it out.  Global memory only ever sees full contiguous rows, where the
+// per-thread functors (KLinksToAos / KLinksFromAos) touch the AoS side in 16-byte pieces at a 144-byte stride.
+__device__ __forceinline__ unsigned lq_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lq_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lq_smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void lq_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lq_mbar_wait(unsigned long long* bar, unsigned phase) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(lq_smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void lq_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   lq_smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(lq_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void lq_bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(lq_smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+template <int TO_AOS>
+__global__ void __launch_bounds__(128)
+    lq_aos4_tma_kernel(LqGeom g, cx* __restrict__ U, double* __restrict__ aos) {
+  extern __shared__ __align__(128) unsigned char lq_aos_smem[];
+  __shared__ __align__(8) unsigned long long bar;
+  const int e0 = g.ext[0], ne0 = g.ne0;
+  const unsigned row_bytes = (unsigned)e0 * 576u;
+  cx* soa = (cx*)lq_aos_smem;
+  cx* lin = (cx*)(lq_aos_smem + row_bytes);
+  const int rowi = blockIdx.x;
+  int q = rowi / g.ext[1];
+  const int x1 = rowi - q * g.ext[1] + g.ghost[1];
+  int r2 = q;
+  q = r2 / g.ext[2];
+  const int x2 = r2 - q * g.ext[2] + g.ghost[2];
+  const int x3 = q + g.ghost[3];
+  const lq_i64 base = (lq_i64)x1 * g.sstride[1] + (lq_i64)x2 * g.sstride[2] + (lq_i64)x3 * g.sstride[3];
+  cx* gsoa = U + (base >> 5) * (36 * 32);
+  cx* gaos = (cx*)aos + (lq_i64)rowi * e0 * 36;
+  if (threadIdx.x == 0) lq_mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    lq_mbar_expect_tx(&bar, row_bytes);
+    lq_bulk_g2s(TO_AOS ? soa : lin, TO_AOS ? gsoa : gaos, row_bytes, &bar);
+  }
+  lq_mbar_wait(&bar, 0);
+  for (int e = threadIdx.x; e < e0 * 36; e += 128) {
+    const int lane = e & 31, pc = e >> 5;   // pc = chunk * 36 + plane
+    const int c = pc / 36, plane = pc - c * 36;
+    const int slot = c * 32 + lane;
+    const int x0 = slot < ne0 ? 2 * slot : 2 * (slot - ne0) + 1;
+    const int dir = plane / 9, k = plane - dir * 9;
+    const int rr = k / 3, cc = k - rr * 3;
+    const int a = (x0 * 4 + dir) * 9 + cc * 3 + rr;  // nalgebra ArrayStorage: column-major
+    if (TO_AOS) lin[a] = soa[e];
+    else soa[e] = lin[a];
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+  __syncthreads();
+  if (threadIdx.x == 0) lq_bulk_s2g(TO_AOS ? (void*)gaos : (void*)gsoa, TO_AOS ? lin : soa, row_bytes);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // launchers used by lq_capi.cu (D = 4; 32-bit element indices: fields below 2^31 elements, else the generic path)
 static inline bool lq_tuned_ok(const LqGeom& g) {
   return g.D == 4 && g.nchunk * 32 * 36 < ((lq_i64)1 << 31) && g.vol < ((lq_i64)1 << 31);
@@ -636,6 +718,23 @@ static inline cudaError_t lq_tuned_sweep(cudaStream_t st, const LqGeom& g, cx* U
     lq_sweep4_kernel<BLOCK, 3, 0><<<nb, BLOCK, 0, st>>>(g, U, mu, parity, flags, or_kind, coupling, seed, counter);
   else
     lq_sweep4_kernel<BLOCK, 3, 1><<<nb, BLOCK, 0, st>>>(g, U, mu, parity, flags, or_kind, coupling, seed, counter);
+  return cudaGetLastError();
+}
+// links AoS <-> SoA through bulk (TMA) copies of whole rows; false: geometry not covered (use the per-thread functors)
+static inline bool lq_tuned_aos_ok(const LqGeom& g) { return g.D == 4 && g.ext[0] % 32 == 0 && g.ext[0] <= 128; }
+static inline cudaError_t lq_tuned_links_aos(cudaStream_t st, const LqGeom& g, cx* U, double* aos, bool to_aos) {
+  const unsigned smem = 2u * (unsigned)g.ext[0] * 576u;
+  const unsigned rows = (unsigned)(g.vol / g.ext[0]);
+  cudaError_t e;
+  if (to_aos) {
+    e = cudaFuncSetAttribute(lq_aos4_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lq_aos4_tma_kernel<1><<<rows, 128, smem, st>>>(g, U, aos);
+  } else {
+    e = cudaFuncSetAttribute(lq_aos4_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    lq_aos4_tma_kernel<0><<<rows, 128, smem, st>>>(g, U, aos);
+  }
   return cudaGetLastError();
 }
 // per-block partial sums of the plaquette terms: ceil(vol / 32) blocks x 3 doubles

@@ -154,6 +154,8 @@ def test_decomposed_matches_oracle_nccl():
         res = _run(2, "nccl", 4, [8, 8, 8, 16], [1, 1, 1, 2], transport)
         _check(res)
         assert res["transport"] == ("p2p" if transport == "p2p" else "nccl-callbacks"), res["transport"]
+        if transport == "p2p":  # x0 extent 32: the bulk-copy (TMA) AoS <-> SoA row kernels on a lattice with ghost layers
+            _check(_run(2, "nccl", 4, [32, 4, 4, 4], [1, 1, 1, 2], transport))
         if n >= 4:
             res = _run(4, "nccl", 4, [8, 8, 8, 8], [1, 1, 2, 2], transport)
             _check(res)
