@@ -177,13 +177,19 @@ __device__ __forceinline__ M3 lq_ld36(const cx* __restrict__ U, int slot, int di
 // L2 prefetch of one link matrix of the warp (9 planes x the 128-byte lines its slots touch): a hint, two instructions per
 // thread.  The lanes of every group of 8 consecutive slots share one line per plane; lane k asks for plane k & 7, all
 // lanes for plane 8, so every (plane, line) pair is requested once or more whatever the rotation of lanes inside a row.
+template <int L1 = 0>
 __device__ __forceinline__ void lq_pf36(const cx* __restrict__ U, int slot, int dir) {
   const int e = ((slot >> 5) * 36 + dir * 9) * 32 + (slot & 31);
   const cx* b = U + e;
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (threadIdx.x & 7) * 32));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(b + 8 * 32));
+  if (L1) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(b + (threadIdx.x & 7) * 32));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(b + 8 * 32));
+  } else {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (threadIdx.x & 7) * 32));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b + 8 * 32));
+  }
 }
-// FLAGS: 1 = visit nu so that direction 3 (first touched from DRAM by most blocks) comes last, 2 = streaming
+// FLAGS: 32 / 128 = L2 / L1 prefetch of the next (half) stage (both measured slower), 1 = visit nu so that direction 3 (first touched from DRAM by most blocks) comes last, 2 = streaming
 // (evict-first) accesses for E and U', 4 = FAKE neighbours (perfect-locality bound, kbench only: wrong results)
 template <int BLOCK, int FUSED, int FLAGS, int PUSH>
 __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restrict__ U, cx* __restrict__ Unew,
@@ -255,11 +261,22 @@ __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restric
     {  // up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)
       M3 a = lq_ld36(U, pm, nu);
       M3 b = lq_ld36(U, p + upn, mu);
+      if (FLAGS & 128) {  // L1 prefetch half a stage ahead: the three operands of the down staple
+        lq_pf36<1>(U, p + dnn, mu);
+        lq_pf36<1>(U, pm + dnn, nu);
+        lq_pf36<1>(U, p + dnn, nu);
+      }
       M3 t = m3_mul_nd(a, b);
       M3 c = lq_ld36(U, p, nu);
       m3_fma_nd(acc, t, c);
     }
     {  // down:  (U_mu(x-nu) U_nu(x+mu-nu))^+ U_nu(x-nu)
+      if ((FLAGS & 128) && j < 3) {  // ... and of the next up staple
+        const int n2 = (FLAGS & 1) ? (j + (j >= mu ? 1 : 0)) : ((mu + j + 1) & 3);
+        lq_pf36<1>(U, pm, n2);
+        lq_pf36<1>(U, p + lq_sel4(n2, up0, up1, up2, up3), mu);
+        lq_pf36<1>(U, p, n2);
+      }
       M3 a = lq_ld36(U, p + dnn, mu);
       M3 b = lq_ld36(U, pm + dnn, nu);
       M3 t = m3_mul_nn(a, b);

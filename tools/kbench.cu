@@ -289,6 +289,9 @@ int main(int argc, char** argv) {
   V4F(128, 3, 4, -1);
   V4F(128, 3, 34, -1);
   V4F(128, 3, 32, -1);
+  V4F(128, 3, 130, -1);
+  V4F(128, 3, 130, 0);
+  V4F(128, 2, 130, -1);
 #define V5(BLOCK, MINB, PIPE)                                                                                      \
   vs.push_back({std::string("v5 pipelined block=" #BLOCK " minb=" #MINB " pipe=" #PIPE),                            \
                 [&] {                                                                                               \
