@@ -52,10 +52,15 @@ enum {
                                  (results are bit-identical either way; this only changes the launch count)    */
   LQ_FLAG_GENERIC_KERNELS = 8, /* use the dimension-generic functor kernels even where a tuned D = 4 kernel exists
                                  (the parity tests run both; results agree to rounding of the staple order)   */
-  LQ_FLAG_GAUSS_FUSED = 4     /* lq_gauss_project(_step): one fused kernel per iteration (projection step + Gauss
+  LQ_FLAG_GAUSS_FUSED = 4,    /* lq_gauss_project(_step): one fused kernel per iteration (projection step + Gauss
                                  field of the projected E, backward neighbours recomputed: 1376 instead of 2208
                                  B/site but 32 instead of 20 matrix products/site) instead of two passes.  Same
                                  results; measured slower on B200 (0.49 vs 0.43 ms at 32^4), so off by default */
+  LQ_FLAG_UNIFORM_DIRECTION = 16 /* heat bath: draw the direction of the SU(2) vector uniformly on the sphere; default
+                                 restates distribution.rs:199-219 as coded (a normalised Uniform(-1,1)^3 sample, which
+                                 over-weights the cube diagonals).  With LQ_FLAG_PAULI3_FIXED and coupling_scale = 1/CA
+                                 the sweep is the textbook Cabibbo-Marinari / Kennedy-Pendleton heat bath of the Wilson
+                                 action (tests/test_physics.py: <P>/3 = 0.5937 at beta = 6)                          */
 };
 
 const char* lq_strerror(int code);

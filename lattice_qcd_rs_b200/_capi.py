@@ -24,7 +24,7 @@ ERRORS = {
 }
 SYNC_SYNC, LEAP_LEAP, SYNC_LEAP, LEAP_SYNC, SYMPLECTIC = range(5)
 OR_ROTATION, OR_REVERSE = 0, 1
-FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED, FLAG_GENERIC_KERNELS = 1, 2, 4, 8
+FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED, FLAG_GENERIC_KERNELS, FLAG_UNIFORM_DIRECTION = 1, 2, 4, 8, 16
 INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_OMELYAN = 0, 1
 OMELYAN_LAMBDA = 0.1931833275037836  # second-order minimum-norm coefficient (Omelyan, Mryglod, Folk 2003)
 

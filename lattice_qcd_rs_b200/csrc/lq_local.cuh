@@ -236,7 +236,8 @@ LQ_HD double lq_heat_bath_norm(double param_exp, LqStream& rng) {
   }
   return 1.0;
 }
-// HeatBathDistribution -> 2x2 matrix, distribution.rs:199-219 (direction = normalised cube sample, as coded)
+// HeatBathDistribution -> 2x2 matrix, distribution.rs:199-219 (direction = normalised cube sample, as coded; with
+// LQ_FLAG_UNIFORM_DIRECTION cube samples outside the unit ball are rejected => uniform on the sphere)
 LQ_HD M2 lq_heat_bath_matrix(double param_exp, LqStream& rng, int flags) {
   double x0 = lq_heat_bath_norm(param_exp, rng);
   double xu[3], n;
@@ -246,7 +247,7 @@ LQ_HD M2 lq_heat_bath_matrix(double param_exp, LqStream& rng, int flags) {
     xu[1] = rng.uniform_pm1();
     xu[2] = rng.uniform_pm1();
     n = sqrt(xu[0] * xu[0] + xu[1] * xu[1] + xu[2] * xu[2]);
-  } while (n <= LQ_EPS && ++guard < LQ_KP_MAX_ITER);
+  } while ((n <= LQ_EPS || ((flags & 16) && n > 1.0)) && ++guard < LQ_KP_MAX_ITER);  // 16: LQ_FLAG_UNIFORM_DIRECTION
   double sc = sqrt(1.0 - x0 * x0);
   double x[3] = {xu[0] / n * sc, xu[1] / n * sc, xu[2] / n * sc};
   return lq_matrix_from_vec(x0, x, flags);

@@ -636,6 +636,10 @@ inline Mat3 random_su3(R& rng) {
 //   PAULI_3 = diag(1, 1) (su2.rs:39-45; its doc comment says diag(1,-1)), which makes every
 //   complex_matrix_from_vec output non-unitary when x_3 != 0.
 constexpr int FLAG_PAULI3_FIXED = 1;
+//   FLAG_UNIFORM_DIRECTION: draw the direction of the heat-bath SU(2) vector uniformly on the sphere (reject cube
+//   samples outside the unit ball).  Default (0) restates distribution.rs:199-219 AS CODED: a Uniform(-1,1)^3 sample
+//   normalised to unit length, which over-weights the cube diagonals (not the heat-bath conditional distribution).
+constexpr int FLAG_UNIFORM_DIRECTION = 16;
 inline int g_flags = 0;
 constexpr int KP_MAX_ITER = 10000;  // the reference loops forever on NaN parameters; both ports cap and return x0 = 1
 // complex_matrix_from_vec, su2.rs:134-140
@@ -742,7 +746,7 @@ inline Mat2 heat_bath_matrix(double param_exp, R& rng) {
   do {
     for (auto& v : xu) v = rng.uniform_pm1();
     n = std::sqrt(xu[0] * xu[0] + xu[1] * xu[1] + xu[2] * xu[2]);
-  } while (n <= EPS && ++guard < KP_MAX_ITER);
+  } while ((n <= EPS || ((g_flags & FLAG_UNIFORM_DIRECTION) && n > 1.0)) && ++guard < KP_MAX_ITER);
   double sc = std::sqrt(1.0 - x0 * x0);
   double x[3] = {xu[0] / n * sc, xu[1] / n * sc, xu[2] / n * sc};
   return complex_matrix_from_vec(x0, x);

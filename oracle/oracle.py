@@ -101,9 +101,11 @@ class Oracle:
         return self.L.lqo_num_threads()
 
     FLAG_PAULI3_FIXED = 1
+    FLAG_UNIFORM_DIRECTION = 16
 
     def set_flags(self, flags):
-        """Process-global behaviour flags (0 = reference as coded; 1 = true sigma_3)."""
+        """Process-global behaviour flags (0 = reference as coded; 1 = true sigma_3; 16 = sphere-uniform heat-bath
+        direction)."""
         self.L.lqo_set_flags(C.c_int(flags))
 
     def set_num_threads(self, n):
