@@ -75,3 +75,52 @@ def test_uniform_direction_flag_matches_oracle(backend):
     c.links_upload(U)
     c.sweep_heatbath(SEED_RNG, 3, coupling_scale=1.0 / 3.0)
     assert np.abs(c.links_download() - want).max() > 1e-3
+
+
+def _hmc_chain(c, L, dt, n, ntraj, therm, seed):
+    from lattice_qcd_rs_b200 import FLAG_PAULI3_FIXED, FLAG_UNIFORM_DIRECTION, INTEGRATOR_OMELYAN, OMELYAN_LAMBDA
+    c.set_flags(FLAG_PAULI3_FIXED | FLAG_UNIFORM_DIRECTION)
+    c.links_set_random(seed, 0)
+    for k in range(therm):  # thermalise with the textbook heat bath, then switch algorithm
+        c.sweep_heatbath(seed, 1 + k, coupling_scale=1.0 / 3.0)
+    c.set_integrator(INTEGRATOR_OMELYAN, OMELYAN_LAMBDA, True)
+    plaq, dh, acc = [], [], 0
+    for k in range(ntraj):
+        # sigma = 1/sqrt(beta): the momenta of the kinetic term beta E^2/2 (the crate draws 0.5/beta, state.rs:1097);
+        # no Gauss projection; Omelyan steps with the exponential link update (reversible, stays in SU(3))
+        r = c.hmc_trajectory(dt, n, seed, 1000 + k, sigma=1.0 / np.sqrt(c.beta), do_project=False)
+        acc += int(r["accepted"])
+        dh.append(r["h_new"] - r["h_old"])
+        plaq.append(c.average_trace_plaquette().real / 3.0)
+    c.set_integrator()  # back to the reference's integrator
+    return np.array(plaq), np.array(dh), acc / ntraj
+
+
+def test_hmc_creutz_equality(backend):
+    """<exp(-dH)> = 1 for an area-preserving, reversible integrator with momenta drawn from exp(-K): checks force,
+    link update, Hamiltonian reductions and momentum refresh against each other (4^4, runs on the CPU build too)."""
+    c = backend(4, 4, a=1.0, beta=6.0)
+    plaq, dh, acc = _hmc_chain(c, 4, 0.1, 10, 60, 40, SEED_RNG)
+    assert acc > 0.8
+    assert abs(np.mean(np.exp(-dh)) - 1.0) < 0.05, np.mean(np.exp(-dh))
+    assert 0.55 < plaq[20:].mean() < 0.63
+
+
+@pytest.mark.gpu
+def test_hmc_with_textbook_options_reproduces_the_literature_plaquette():
+    """16^4, beta = 6: HMC through lq_hmc_trajectory with the option set of SURVEY 8f-4 (sigma = 1/sqrt(beta), no Gauss
+    projection, Omelyan + exponential link update) samples the Wilson ensemble: <P>/3 = 0.59374 +- 0.00008 measured
+    (profiles/r01ze_hmc_physics_scan.txt) against 0.59368 in the literature.  The crate's own recipe does not: with the
+    Euler link update the same chain runs away to <P>/3 = 0.97 with every trajectory accepted (links leave SU(3))."""
+    import torch
+    assert torch.cuda.is_available()
+    from lattice_qcd_rs_b200 import Context
+    c = Context(4, 16, a=1.0, beta=6.0)
+    plaq, dh, acc = _hmc_chain(c, 16, 0.08, 25, 300, 120, SEED_RNG)
+    v = plaq[60:]
+    nb = 8
+    b = v[:len(v) // nb * nb].reshape(nb, -1).mean(1)
+    err = b.std(ddof=1) / np.sqrt(nb)
+    assert 0.6 < acc <= 1.0
+    assert abs(np.mean(np.exp(-dh)) - 1.0) < 0.2
+    assert abs(v.mean() - 0.5937) < max(4.0 * err, 1.0e-3), (v.mean(), err)
