@@ -858,7 +858,7 @@ static int link_step(lq_ctx* c, const cx* Uin, cx* Uout, double dt, int use_exp)
   return LQ_OK;
 }
 // E += nkick * (dt_e F[U]);  U <- step(U, E_new, dt_u)  in one kernel (second link buffer, then swap)
-static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u) {
+static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u, int use_exp = 0) {
   LQ_TRY(ensure_halo(c, 0));
   LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
 #ifdef LQ_TUNED
@@ -873,7 +873,7 @@ static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u) {
     {
       ProfScope ps2(c, LQ_PROF_EFIELD_LINK_STEP);
       LQ_CHECK(lq_tuned_efield_link_step_push(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u,
-                                              link_coef(c), nkick, (const LqPush*)c->d_push + bi));
+                                              link_coef(c), nkick, (const LqPush*)c->d_push + bi, use_exp));
       c->launches++;
     }
     LQ_TRY(p2p_barrier(c));  // data: their pushes into my ghost layers have landed
@@ -889,7 +889,7 @@ static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u) {
   if (tuned) {
     ProfScope ps(c, LQ_PROF_EFIELD_LINK_STEP);
     LQ_CHECK(lq_tuned_efield_link_step(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u, link_coef(c),
-                                       nkick));
+                                       nkick, use_exp));
     c->launches++;
   } else
 #endif
@@ -897,7 +897,7 @@ static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u) {
     ProfScope ps(c, LQ_PROF_EFIELD_LINK_STEP);
     LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g),
                                    KEfieldLinkStep<DD>{c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u, link_coef(c),
-                                                       nkick, 0}))));
+                                                       nkick, use_exp}))));
   }
   cx* t = c->U;
   c->U = c->U2;
@@ -991,22 +991,19 @@ int lq_md_n(lq_ctx* c, double dt, int64_t n) {
   if (n <= 0) return LQ_E_ZERO_STEPS;
   LQ_GUARD(c);
   if (c->integ_kind == LQ_INTEGRATOR_SYMPLECTIC_EULER && !c->integ_exp) return lq_symplectic_n(c, dt, n);
+  // every E kick is fused with the link step that follows it (one kernel: force + kick + link update, the new boundary
+  // links pushed to the neighbour ranks); only the closing kick runs alone
   const int ex = c->integ_exp;
   if (c->integ_kind == LQ_INTEGRATOR_SYMPLECTIC_EULER) {
+    for (int64_t k = 0; k < n; ++k) LQ_TRY(efield_link_step(c, k == 0 ? dt / 2.0 : dt, 1, dt, ex));
     LQ_TRY(efield_step(c, dt / 2.0, 1));
-    for (int64_t k = 0; k < n; ++k) {
-      LQ_TRY(link_step(c, c->U, c->U, dt, ex));
-      LQ_TRY(efield_step(c, k + 1 < n ? dt : dt / 2.0, 1));
-    }
   } else {
     const double l = c->integ_lambda;
-    LQ_TRY(efield_step(c, l * dt, 1));
     for (int64_t k = 0; k < n; ++k) {
-      LQ_TRY(link_step(c, c->U, c->U, dt / 2.0, ex));
-      LQ_TRY(efield_step(c, (1.0 - 2.0 * l) * dt, 1));
-      LQ_TRY(link_step(c, c->U, c->U, dt / 2.0, ex));
-      LQ_TRY(efield_step(c, k + 1 < n ? 2.0 * l * dt : l * dt, 1));
+      LQ_TRY(efield_link_step(c, k == 0 ? l * dt : 2.0 * l * dt, 1, dt / 2.0, ex));
+      LQ_TRY(efield_link_step(c, (1.0 - 2.0 * l) * dt, 1, dt / 2.0, ex));
     }
+    LQ_TRY(efield_step(c, l * dt, 1));
   }
   c->t += n;
   return LQ_OK;

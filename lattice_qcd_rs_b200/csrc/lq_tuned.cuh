@@ -312,7 +312,7 @@ __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restric
     else E[ee + k * 32] = cmk(e.e[2 * k], e.e[2 * k + 1]);
   }
   if (FUSED) {
-    M3 un = lq_link_update<4>(u, e, dt_u, c_u, 0);
+    M3 un = lq_link_update<4>(u, e, dt_u, c_u, (FLAGS & 256) ? 1 : 0);  // 256: U <- exp(i dt E) U instead of Euler
     cx* b = Unew + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
@@ -720,10 +720,14 @@ static inline cudaError_t lq_tuned_efield_step(cudaStream_t st, const LqGeom& g,
   return cudaGetLastError();
 }
 static inline cudaError_t lq_tuned_efield_link_step(cudaStream_t st, const LqGeom& g, const cx* U, cx* Unew, cx* E,
-                                                    double coef, double dt_e, double dt_u, double c_u, int nkick) {
+                                                    double coef, double dt_e, double dt_u, double c_u, int nkick,
+                                                    int use_exp = 0) {
   constexpr int BLOCK = 128;
-  lq_md4_kernel<BLOCK, 3, 1, 2><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e,
-                                                                                                dt_u, c_u, nkick, nullptr, 0);
+  const unsigned nb = (unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4));
+  if (use_exp)
+    lq_md4_kernel<BLOCK, 3, 1, 2 | 256><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0);
+  else
+    lq_md4_kernel<BLOCK, 3, 1, 2><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0);
   return cudaGetLastError();
 }
 static inline cudaError_t lq_tuned_sweep(cudaStream_t st, const LqGeom& g, cx* U, int kind /*0 hb, 1 or*/, int mu, int parity,
@@ -765,12 +769,15 @@ static inline cudaError_t lq_tuned_plaquette(cudaStream_t st, const LqGeom& g, c
 // fused force + E kick + link step + halo push of the new boundary links into the neighbours' ghost layers
 static inline cudaError_t lq_tuned_efield_link_step_push(cudaStream_t st, const LqGeom& g, const cx* U, cx* Unew, cx* E,
                                                          double coef, double dt_e, double dt_u, double c_u, int nkick,
-                                                         const LqPush* d_ps) {
+                                                         const LqPush* d_ps, int use_exp = 0) {
   constexpr int BLOCK = 128;
   const lq_i64 slice = g.vol / g.ext[3];
   const int bps = (g.ghost[3] && slice % (BLOCK / 4) == 0) ? (int)(slice / (BLOCK / 4)) : 0;
-  lq_md4_kernel<BLOCK, 3, 1, 2, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(
-      g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
+  const unsigned nb = (unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4));
+  if (use_exp)
+    lq_md4_kernel<BLOCK, 3, 1, 2 | 256, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
+  else
+    lq_md4_kernel<BLOCK, 3, 1, 2, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
   return cudaGetLastError();
 }
 

@@ -77,6 +77,16 @@ def _worker(rank, world, port, backend, D, gext, proc_grid, q, transport="p2p"):
             Uo, Eo = o.integrate(U, E, name, 0.01)
             res["int_" + name] = max(rel(dc.gather(c.links_download(), 18), Uo),
                                      rel(dc.gather(c.efield_download(), 8), Eo))
+        # integrator options (lq_set_integrator / lq_md_n): Omelyan steps with the exponential link update, every
+        # kick fused with the link step that follows it (the push variant of the fused kernel on decomposed contexts)
+        c.links_upload(dc.scatter(U, 18))
+        c.efield_upload(dc.scatter(E, 8))
+        c.set_integrator(1, 0.1931833275037836, True)
+        c.md_n(0.02, 3)
+        c.set_integrator()
+        Uo, Eo = o.md_n(U, E, 0.02, 3, kind=1, use_exp=True)
+        res["omelyan_U"] = rel(dc.gather(c.links_download(), 18), Uo)
+        res["omelyan_E"] = rel(dc.gather(c.efield_download(), 8), Eo)
         # full HMC trajectory with Philox momenta: decomposition-independent streams, same accept decision
         c.links_upload(dc.scatter(U, 18))
         r = c.hmc_trajectory(0.01, 5, SEED, 3)
