@@ -44,7 +44,9 @@ enum {
 /* integrator compositions, symplectic_euler_rayon.rs:120-252 */
 enum { LQ_SYNC_SYNC = 0, LQ_LEAP_LEAP = 1, LQ_SYNC_LEAP = 2, LQ_LEAP_SYNC = 3, LQ_SYMPLECTIC = 4 };
 /* over-relaxation flavours, overrelaxation.rs:86-98 / 158-171 */
-enum { LQ_OR_ROTATION = 0, LQ_OR_REVERSE = 1 };
+/* 0, 1: OverrelaxationSweepRotation / Reverse (overrelaxation.rs:86-98, 158-171; U(3)-valued, as the crate);
+ * 2: option beyond the crate -- Brown-Woch reflections in the three SU(2) sub-groups of the heat bath (stays in SU(3)) */
+enum { LQ_OR_ROTATION = 0, LQ_OR_REVERSE = 1, LQ_OR_SU2_SUBGROUPS = 2 };
 /* behaviour flags (lq_set_flags) */
 enum {
   LQ_FLAG_PAULI3_FIXED = 1,   /* use sigma_3 = diag(1,-1); default restates su2.rs:39-45 as coded (diag(1,1)) */

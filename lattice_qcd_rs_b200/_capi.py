@@ -23,7 +23,7 @@ ERRORS = {
     -6: "LQ_E_GAUSS_DIVERGED", -7: "LQ_E_ZERO_STEPS", -8: "LQ_E_NOSNAPSHOT", -9: "LQ_E_NODEVICE",
 }
 SYNC_SYNC, LEAP_LEAP, SYNC_LEAP, LEAP_SYNC, SYMPLECTIC = range(5)
-OR_ROTATION, OR_REVERSE = 0, 1
+OR_ROTATION, OR_REVERSE, OR_SU2_SUBGROUPS = 0, 1, 2
 FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED, FLAG_GENERIC_KERNELS, FLAG_UNIFORM_DIRECTION = 1, 2, 4, 8, 16
 INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_OMELYAN = 0, 1
 OMELYAN_LAMBDA = 0.1931833275037836  # second-order minimum-norm coefficient (Omelyan, Mryglod, Folk 2003)

@@ -1175,7 +1175,7 @@ int lq_sweep_heatbath(lq_ctx* c, uint64_t seed, uint64_t counter, double couplin
   return LQ_OK;
 }
 int lq_sweep_overrelax(lq_ctx* c, int kind) {
-  if (!c || (kind != LQ_OR_ROTATION && kind != LQ_OR_REVERSE)) return LQ_E_BADARG;
+  if (!c || (kind != LQ_OR_ROTATION && kind != LQ_OR_REVERSE && kind != LQ_OR_SU2_SUBGROUPS)) return LQ_E_BADARG;
   if (!c->even_extents) return LQ_E_ODD_EXTENT;
   LQ_GUARD(c);
   for (int d = 0; d < c->g.D; ++d)

@@ -273,7 +273,8 @@ LQ_HD M2 lq_heat_bath_su2(const M2& stap, double coupling, LqStream& rng, int fl
 // rows (ia, ib) of x * cur that the embedded 2x2 matrix x changes.  Every entry is the same k-ascending FMA chain as in
 // m3_mul_nn -- the skipped terms are products with the exact 0 / 1 entries of the embedding -- so the bits are those of
 // the two full 3x3 products (44 % of their FMAs).
-LQ_HD M3 lq_heat_bath_link(const M3& u, const M3& a, double coupling, LqStream& rng, int flags) {
+template <class Rule>
+LQ_HD M3 lq_subgroup_update(const M3& u, const M3& a, Rule rule) {
   M3 cur = u;
 #pragma unroll 1
   for (int which = 0; which < 3; ++which) {
@@ -295,7 +296,7 @@ LQ_HD M3 lq_heat_bath_link(const M3& u, const M3& a, double coupling, LqStream& 
       cfma(w.c, rb[k], ca[k]);
       cfma(w.d, rb[k], cb[k]);
     }
-    const M2 x = lq_heat_bath_su2(lq_project_to_su2_unorm(w), coupling, rng, flags);
+    const M2 x = rule(lq_project_to_su2_unorm(w));
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       cx na = cmk(0.0, 0.0), nb = cmk(0.0, 0.0);
@@ -310,6 +311,35 @@ LQ_HD M3 lq_heat_bath_link(const M3& u, const M3& a, double coupling, LqStream& 
   }
   return cur;
 }
+struct LqHeatBathRule {
+  double coupling;
+  LqStream* rng;
+  int flags;
+  LQ_HD M2 operator()(const M2& p) const { return lq_heat_bath_su2(p, coupling, *rng, flags); }
+};
+LQ_HD M3 lq_heat_bath_link(const M3& u, const M3& a, double coupling, LqStream& rng, int flags) {
+  return lq_subgroup_update(u, a, LqHeatBathRule{coupling, &rng, flags});
+}
+// Option beyond the crate: over-relaxation inside the same three SU(2) sub-groups (Brown-Woch): with
+// m = project(w)/k in SU(2), left-multiplying by (m^dagger)^2 reflects the block to m^dagger -- Re tr W unchanged, the
+// link stays in SU(3) (the crate's SVD variants return U(3) matrices, overrelaxation.rs:96-97).
+struct LqOverrelaxSu2Rule {
+  LQ_HD M2 operator()(const M2& p) const {
+    const double k = sqrt(m2_det(p).x);
+    M2 r;
+    if (!lq_is_normal(k)) {
+      r.a = r.d = cmk(1.0, 0.0);
+      r.b = r.c = cmk(0.0, 0.0);
+      return r;
+    }
+    M2 v = m2_adj(p);
+    v.a = cmk(v.a.x / k, v.a.y / k);
+    v.b = cmk(v.b.x / k, v.b.y / k);
+    v.c = cmk(v.c.x / k, v.c.y / k);
+    v.d = cmk(v.d.x / k, v.d.y / k);
+    return m2_mul(v, v);
+  }
+};
 // MetropolisHastingsSweep::potential_modif, metropolis_hastings_sweep.rs:126-143
 LQ_HD M3 lq_metropolis_proposal(const M3& old_link, int n_update, double spread, LqStream& rng, int flags) {
   M3 nl = old_link;
@@ -386,6 +416,7 @@ LQ_HD M3 lq_reverse(const M3& a) {
 // OverrelaxationSweepRotation::get_modif, overrelaxation.rs:86-98:  rot U^dagger rot,  rot = u v^dagger of svd(A^dagger)
 // OverrelaxationSweepReverse::get_modif, overrelaxation.rs:158-171: u reverse(u^dagger U v) v^dagger
 LQ_HD M3 lq_overrelax_link(const M3& ulink, const M3& stap, int kind) {
+  if (kind == 2) return lq_subgroup_update(ulink, stap, LqOverrelaxSu2Rule{});
   M3 u, v;
   lq_svd3(m3_adj(stap), u, v);
   if (kind == 0) {

@@ -679,6 +679,12 @@ class OverrelaxationSweepReverse(_Overrelax):
     KIND = _capi.OR_REVERSE
 
 
+class OverrelaxationSweepSu2(_Overrelax):
+    """Not in the crate: Brown-Woch reflections in the three SU(2) sub-groups of the heat bath; unlike the
+    two SVD variants above (U(3)-valued, overrelaxation.rs:96-97) the links stay in SU(3)."""
+    KIND = _capi.OR_SU2_SUBGROUPS
+
+
 class MetropolisHastingsSweep(MonteCarlo):
     """metropolis_hastings_sweep.rs:41-174."""
 

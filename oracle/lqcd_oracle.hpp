@@ -897,13 +897,34 @@ inline void sweep_heatbath(const Lattice& L, double* U, double beta, double coup
     }
   });
 }
+// Option beyond the crate: over-relaxation inside the three SU(2) sub-groups (Brown-Woch reflections on
+// the Cabibbo-Marinari blocks of heat_bath.rs:90-109).  For each block: w = 2x2 block of cur*A, m = project(w)/k in SU(2),
+// left-multiply by (m^dagger)^2, which maps the block to its reflection m^dagger: Re tr unchanged, links stay in SU(3)
+// (the crate's SVD variants return U(3) matrices, overrelaxation.rs:96-97).
+inline Mat3 overrelax_su2(const Mat3& ulink, const Mat3& stap) {
+  Mat3 cur = ulink;
+  for (int which = 0; which < 3; ++which) {
+    Mat2 p = project_to_su2_unorm(sub_block(cur * stap, which));
+    double k = std::sqrt(det(p).re);
+    if (!is_normal(k)) continue;
+    Mat2 v = adj(p);
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j) v.m[i][j] = v.m[i][j] / k;
+    Mat2 x = v * v;
+    cur = (which == 0 ? get_r(x) : which == 1 ? get_s(x) : get_t(x)) * cur;
+  }
+  return cur;
+}
+inline Mat3 overrelax_any(const Mat3& u, const Mat3& a, int kind) {
+  return kind == 0 ? overrelax_rotation(u, a) : kind == 1 ? overrelax_reverse(u, a) : overrelax_su2(u, a);
+}
 // OverrelaxationSweep{Rotation,Reverse}::next_element_default, overrelaxation.rs:100-110, 173-184
-inline void sweep_overrelax(const Lattice& L, double* U, int kind /*0 rotation, 1 reverse*/, int order) {
+inline void sweep_overrelax(const Lattice& L, double* U, int kind /*0 rotation, 1 reverse, 2 SU(2) sub-groups*/, int order) {
   for_each_link(L, order, [&](int64_t x, int d) {
     int64_t l = x * L.D + d;
     Mat3 u = load3(U + l * 18);
     Mat3 a = staple(L, U, x, d);
-    store3(U + l * 18, kind == 0 ? overrelax_rotation(u, a) : overrelax_reverse(u, a));
+    store3(U + l * 18, overrelax_any(u, a, kind));
   });
 }
 // MetropolisHastingsSweep::next_element_default, metropolis_hastings_sweep.rs:145-174

@@ -64,7 +64,7 @@ void lqo_svd3(const double* a18, double* u18, double* s3, double* v18) {
 }
 void lqo_overrelax_link(const double* u18, const double* staple18, int kind, double* out18) {
   Mat3 u = load3(u18), a = load3(staple18);
-  store3(out18, kind == 0 ? overrelax_rotation(u, a) : overrelax_reverse(u, a));
+  store3(out18, overrelax_any(u, a, kind));
 }
 void lqo_project_to_su2_unorm(const double* in8, double* out8) {
   // 2x2 row-major (re,im) in / out

@@ -124,3 +124,47 @@ def test_hmc_with_textbook_options_reproduces_the_literature_plaquette():
     assert 0.6 < acc <= 1.0
     assert abs(np.mean(np.exp(-dh)) - 1.0) < 0.2
     assert abs(v.mean() - 0.5937) < max(4.0 * err, 1.0e-3), (v.mean(), err)
+
+
+@pytest.mark.parametrize("D,ext", [(4, [4, 4, 4, 4]), (3, [4, 6, 4])])
+def test_su2_subgroup_overrelaxation(backend, D, ext):
+    """lq_sweep_overrelax(kind = LQ_OR_SU2_SUBGROUPS): parity with the oracle, exactly microcanonical, stays in SU(3)
+    (the crate's SVD variants are U(3)-valued)."""
+    from lattice_qcd_rs_b200 import OR_ROTATION, OR_SU2_SUBGROUPS
+    o = Oracle(D, ext, a=1.0, beta=6.0)
+    c = backend(D, ext, a=1.0, beta=6.0)
+    U = o.links_random(SEED_RNG)
+    c.links_upload(U)
+    h0 = c.hamiltonian_links()
+    c.sweep_overrelax(OR_SU2_SUBGROUPS)
+    got = c.links_download()
+    assert np.abs(got - o.sweep_overrelax(U, 2, order=1)).max() <= 1e-9
+    assert np.abs(got - U).max() > 0.1  # it moves the links ...
+    assert abs(c.hamiltonian_links() - h0) <= 1e-11 * abs(h0)  # ... at constant action
+    M = got.reshape(-1, 3, 3, 2)
+    M = (M[..., 0] + 1j * M[..., 1]).transpose(0, 2, 1)
+    assert np.abs(M @ M.conj().transpose(0, 2, 1) - np.eye(3)).max() < 1e-12
+    assert np.abs(np.linalg.det(M) - 1.0).max() < 1e-12
+    c.links_upload(U)
+    c.sweep_overrelax(OR_ROTATION)
+    R = c.links_download().reshape(-1, 3, 3, 2)
+    R = (R[..., 0] + 1j * R[..., 1]).transpose(0, 2, 1)
+    assert np.abs(np.linalg.det(R) - 1.0).max() > 1e-3  # the crate's rotation variant leaves SU(3) (a U(1) phase)
+
+
+def test_heatbath_plus_su2_overrelaxation_keeps_the_ensemble(backend):
+    """1 heat-bath + 2 over-relaxation sweeps per iteration (the usual mix): same plaquette, fewer iterations."""
+    from lattice_qcd_rs_b200 import FLAG_PAULI3_FIXED, FLAG_UNIFORM_DIRECTION, OR_SU2_SUBGROUPS
+    c = backend(4, 8, a=1.0, beta=6.0)
+    c.set_flags(FLAG_PAULI3_FIXED | FLAG_UNIFORM_DIRECTION)
+    c.links_set_random(SEED_RNG, 0)
+    vals = []
+    for k in range(70):
+        c.sweep_heatbath(SEED_RNG, 1 + k, coupling_scale=1.0 / 3.0)
+        c.sweep_overrelax(OR_SU2_SUBGROUPS)
+        c.sweep_overrelax(OR_SU2_SUBGROUPS)
+        if k >= 30:
+            vals.append(c.average_trace_plaquette().real / 3.0)
+    v = np.array(vals)
+    err = 2.0 * v.std(ddof=1) / np.sqrt(v.size)
+    assert abs(v.mean() - 0.5937) < max(3.0 * err, 2.5e-3), (v.mean(), err)
