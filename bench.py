@@ -277,6 +277,7 @@ def run_ours(args):
     if world == 1:
         for name, fn, cls in (("heatbath", lambda i: ctx.sweep_heatbath(SEED, 9000 + i), "heatbath"),
                               ("overrelax", lambda i: ctx.sweep_overrelax(0), "overrelax"),
+                              ("overrelax_su2_subgroups", lambda i: ctx.sweep_overrelax(2), "overrelax"),
                               ("metropolis", lambda i: ctx.sweep_metropolis(SEED, 9500 + i), "metropolis")):
             fn(0)
             t = timed(fn, 3)
