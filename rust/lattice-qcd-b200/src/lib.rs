@@ -362,6 +362,48 @@ impl<const D: usize> SymplecticIntegrator<LatticeStateEFSyncCuda<D>, Leap<D>, D>
     }
 }
 
+/// An integrator the crate does not have, offered through the same `SymplecticIntegrator` trait: second-order
+/// minimum-norm (Omelyan) steps `E(l dt) U(dt/2) E((1-2l) dt) U(dt/2) E(l dt)` built from the crate's own two updates
+/// (`integrate_efield`, integrator/mod.rs:240-254; `integrate_link`, :216-233), with `use_exp` replacing the Euler link
+/// update by `U <- exp(i dt E) U` (su3.rs:832-855).  The leap-frog half-step compositions are those of
+/// `SymplecticEulerCuda`.
+#[derive(Clone, Copy, Debug, PartialEq)]
+pub struct OmelyanCuda {
+    pub lambda: Real,
+    pub use_exp: bool,
+}
+
+impl Default for OmelyanCuda {
+    fn default() -> Self {
+        Self { lambda: 0.193_183_327_503_783_6, use_exp: true }
+    }
+}
+
+impl<const D: usize> SymplecticIntegrator<LatticeStateEFSyncCuda<D>, Leap<D>, D> for OmelyanCuda {
+    type Error = CudaError;
+    fn integrate_sync_sync(&self, l: &LatticeStateEFSyncCuda<D>, dt: Real) -> Result<LatticeStateEFSyncCuda<D>, CudaError> {
+        SymplecticEulerCuda.integrate_sync_sync(l, dt)
+    }
+    fn integrate_leap_leap(&self, l: &Leap<D>, dt: Real) -> Result<Leap<D>, CudaError> {
+        SymplecticEulerCuda.integrate_leap_leap(l, dt)
+    }
+    fn integrate_sync_leap(&self, l: &LatticeStateEFSyncCuda<D>, dt: Real) -> Result<Leap<D>, CudaError> {
+        SymplecticEulerCuda.integrate_sync_leap(l, dt)
+    }
+    fn integrate_leap_sync(&self, l: &Leap<D>, dt: Real) -> Result<LatticeStateEFSyncCuda<D>, CudaError> {
+        SymplecticEulerCuda.integrate_leap_sync(l, dt)
+    }
+    fn integrate_symplectic(&self, l: &LatticeStateEFSyncCuda<D>, dt: Real) -> Result<LatticeStateEFSyncCuda<D>, CudaError> {
+        let mut n = l.clone();
+        check(unsafe { ffi::lq_set_integrator(n.ctx(), 1, self.lambda, self.use_exp as i32) })?;
+        let rc = unsafe { ffi::lq_md_n(n.ctx(), dt, 1) };
+        check(unsafe { ffi::lq_set_integrator(n.ctx(), 0, self.lambda, 0) })?;
+        check(rc)?;
+        n.invalidate();
+        Ok(n)
+    }
+}
+
 /// GPU twin of `HybridMonteCarloDiagnostic` (hybrid_monte_carlo.rs:316-471): same constructor arguments and getters.
 pub struct HybridMonteCarloCuda<Rng: rand::Rng> {
     delta_t: Real,
