@@ -107,40 +107,49 @@ SAMPLE_MD, SAMPLE_GAUSS = 4, 7
 
 
 class CpuSample:
-    def __init__(self, ext):
+    def __init__(self, ext, md=SAMPLE_MD, gauss=SAMPLE_GAUSS):
         from oracle.oracle import Oracle
         self.o = o = Oracle(4, ext, a=SPACING, beta=BETA)
         o.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; this arm uses every host core
         self.U = o.links_random(SEED)
         self.E = o.momenta_refresh(SEED, 1)
-        self.ext = ext
+        self.ext, self.md, self.gauss = ext, md, gauss
 
     def step(self):
         o = self.o
-        for _ in range(SAMPLE_GAUSS):
+        for _ in range(self.gauss):
             self.E = o.project_to_gauss_step(self.U, self.E)
-        self.U, self.E = o.integrate(self.U, self.E, "symplectic", DT, n=SAMPLE_MD, literal=True)
+        self.U, self.E = o.integrate(self.U, self.E, "symplectic", DT, n=self.md, literal=True)
 
     def describe(self):
-        return (f"each step = {SAMPLE_MD} symplectic-Euler MD steps (dt={DT}) + {SAMPLE_GAUSS} Gauss-projection iterations "
-                f"on the full {self.ext}^4 beta={BETA} hot lattice (1/25 of the GPU trajectory's 100 : 173 mix; momentum "
-                "refresh, 2x H_total, accept and normalise left out: < 1 % of a trajectory), literal reference loops incl. "
-                "the 28-matmul derivative_e, g++ -O3 -fopenmp on all host cores; C++ restatement of lattice-qcd-rs "
-                "v0.2.1 (oracle/), not the Rust binary")
+        return (f"each step = {self.md} symplectic-Euler MD steps (dt={DT}) + {self.gauss} Gauss-projection iterations "
+                f"on the full {self.ext}^4 beta={BETA} hot lattice (the GPU trajectory's 100 : 173 mix scaled down; "
+                "momentum refresh, 2x H_total, accept and normalise left out: < 1 % of a trajectory), literal reference "
+                "loops incl. the 28-matmul derivative_e, g++ -O3 -fopenmp on all host cores; C++ restatement of "
+                "lattice-qcd-rs v0.2.1 (oracle/), not the Rust binary")
 
 
-def cpu_sample(ext, steps=1, warmup=0):
-    """Oracle (C++/OpenMP restatement of the reference loops, literal mode) timed on the host cores."""
+def cpu_sample(ext, steps=1, warmup=0, budget_s=240.0):
+    """Oracle (C++/OpenMP restatement of the reference loops, literal mode) timed on the host cores.  The sample per step
+    shrinks (4+7 -> 2+4 -> 1+2 MD steps + Gauss iterations) when steps x (time of one step) would exceed `budget_s`."""
+    warmup = min(warmup, 1)  # no clock ramp or JIT on the CPU side: one step faults the pages in
     cs = CpuSample(ext)
-    for _ in range(warmup):
-        cs.step()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        cs.step()
-    el = time.perf_counter() - t0
-    val = SAMPLE_MD * cs.o.nl * steps / el
+    cs.step()  # calibration (counts as the warm-up step)
+    t1 = time.perf_counter() - t0
+    for md, gauss in ((2, 4), (1, 2)):
+        if t1 * cs.md / SAMPLE_MD * steps > budget_s:
+            cs.md, cs.gauss = md, gauss
+    if warmup == 0 and steps == 1 and (cs.md, cs.gauss) == (SAMPLE_MD, SAMPLE_GAUSS):
+        el, done = t1, 1  # the calibration step IS the sample (default bench.py run: about 10 s of CPU work)
+    else:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cs.step()
+        el, done = time.perf_counter() - t0, steps
+    val = cs.md * cs.o.nl * done / el
     return dict(value=val, unit="link-updates/s", cores=cs.o.num_threads(), kind="port",
-                sample=cs.describe() + f"; {steps} step(s), {el:.1f} s"), el
+                sample=cs.describe() + f"; {done} step(s), {el:.1f} s"), el
 
 
 def run_reference(args):
