@@ -841,7 +841,7 @@ static int efield_step(lq_ctx* c, double dt, int nkick) {
     LQ_CHECK(lq_tuned_efield_step(c->stream, c->g, c->U, c->E, force_coef(c), dt, nkick));
     c->launches++;
     c->halo_ok[1] = false;
-  c->g_valid = false;
+    c->g_valid = false;
     return LQ_OK;
   }
 #endif
@@ -903,7 +903,6 @@ static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u, int 
   c->U = c->U2;
   c->U2 = t;
   c->halo_ok[0] = false;
-  c->g_valid = false;
   c->halo_ok[1] = false;
   c->g_valid = false;
   return LQ_OK;
@@ -930,7 +929,7 @@ int lq_integrate(lq_ctx* c, int kind, double dt) {
       c->U = c->U2;
       c->U2 = t;
       c->halo_ok[0] = false;
-  c->g_valid = false;
+      c->g_valid = false;
       c->t += 1;
       return LQ_OK;
     }
@@ -1170,7 +1169,7 @@ int lq_sweep_heatbath(lq_ctx* c, uint64_t seed, uint64_t counter, double couplin
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2,
                                      KHeatBath<DD>{c->g, c->U, d, p, c->flags, c->beta * coupling_scale, seed, counter}))));
       c->halo_ok[0] = false;
-  c->g_valid = false;
+      c->g_valid = false;
     }
   return LQ_OK;
 }
@@ -1190,7 +1189,7 @@ int lq_sweep_overrelax(lq_ctx* c, int kind) {
 #endif
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2, KOverrelax<DD>{c->g, c->U, d, p, kind}))));
       c->halo_ok[0] = false;
-  c->g_valid = false;
+      c->g_valid = false;
     }
   return LQ_OK;
 }
@@ -1210,7 +1209,7 @@ int lq_sweep_metropolis(lq_ctx* c, uint64_t seed, uint64_t counter, double sprea
       acc[0] += c->h_result[0];
       acc[1] += c->h_result[1];
       c->halo_ok[0] = false;
-  c->g_valid = false;
+      c->g_valid = false;
     }
   LQ_TRY(global_sum(c, acc, 2));
   if (n_accept) *n_accept = (int64_t)(acc[0] + 0.5);
@@ -1239,7 +1238,6 @@ int lq_restore(lq_ctx* c) {
   c->t = c->snap_t;
   c->halo_ok[0] = c->halo_ok[1] = false;
   c->g_valid = false;
-  c->g_valid = false;
   return LQ_OK;
 }
 int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint64_t counter, double sigma,
@@ -1266,7 +1264,7 @@ int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint
   if (!ok) {
     LQ_TRY(rt_copy(c->U, c->snapU, c->u_bytes(), D2D, c->stream));
     c->halo_ok[0] = false;
-  c->g_valid = false;
+    c->g_valid = false;
     c->t = t0;
   }
   if (h_old) *h_old = h0;
