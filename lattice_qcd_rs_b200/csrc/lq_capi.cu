@@ -98,6 +98,7 @@ struct lq_ctx {
   LqGeom g;
   double a, beta, CA;
   int flags;
+  bool g_pp_safe;  // the last Gauss-field evaluation was the two-pass peer-memory one (see gauss_field)
   int integ_kind, integ_exp;  // lq_set_integrator: what lq_md_n / lq_hmc_trajectory run (0, 0 = the reference's)
   double integ_lambda;
   int64_t t;
@@ -858,7 +859,8 @@ static int link_step(lq_ctx* c, const cx* Uin, cx* Uout, double dt, int use_exp)
   return LQ_OK;
 }
 // E += nkick * (dt_e F[U]);  U <- step(U, E_new, dt_u)  in one kernel (second link buffer, then swap)
-static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u, int use_exp = 0) {
+// chain: the previous operation on this context was the same fused step (inside one lq_symplectic_n / lq_md_n loop)
+static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u, int use_exp = 0, bool chain = false) {
   LQ_TRY(ensure_halo(c, 0));
   LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
 #ifdef LQ_TUNED
@@ -869,7 +871,11 @@ static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u, int 
     for (int b = 0; b < LQ_P2P_NBUF - 1; ++b)
       if (c->own[b] == c->U2) bi = b;
     if (bi < 0 || !c->d_push) return LQ_E_COMM;
-    LQ_TRY(p2p_barrier(c));  // ready: the neighbours are done reading the ghost layers this kernel overwrites
+    // ready: the neighbours are done reading the ghost layers this kernel overwrites.  Inside a chain of fused steps
+    // the two link buffers alternate, so the ghosts written now were last read by the neighbours' step BEFORE the
+    // previous one -- and a neighbour only arrived at the previous step's data barrier (which this rank has passed)
+    // after that kernel had finished: one barrier per step is enough.
+    if (!chain) LQ_TRY(p2p_barrier(c));
     {
       ProfScope ps2(c, LQ_PROF_EFIELD_LINK_STEP);
       LQ_CHECK(lq_tuned_efield_link_step_push(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u,
@@ -966,7 +972,7 @@ int lq_symplectic_n(lq_ctx* c, double dt, int64_t n) {
   // n x [E(dt/2) U(dt) E(dt/2)]: the trailing kick of step k and the leading kick of step k+1 see the same links,
   // so the force is evaluated once and applied twice (same rounding sequence); each kick is fused with the link
   // step that follows it.
-  for (int64_t k = 0; k < n; ++k) LQ_TRY(efield_link_step(c, dt / 2.0, k == 0 ? 1 : 2, dt));
+  for (int64_t k = 0; k < n; ++k) LQ_TRY(efield_link_step(c, dt / 2.0, k == 0 ? 1 : 2, dt, 0, k > 0));
   LQ_TRY(efield_step(c, dt / 2.0, 1));
   c->t += n;
   return LQ_OK;
@@ -994,13 +1000,13 @@ int lq_md_n(lq_ctx* c, double dt, int64_t n) {
   // links pushed to the neighbour ranks); only the closing kick runs alone
   const int ex = c->integ_exp;
   if (c->integ_kind == LQ_INTEGRATOR_SYMPLECTIC_EULER) {
-    for (int64_t k = 0; k < n; ++k) LQ_TRY(efield_link_step(c, k == 0 ? dt / 2.0 : dt, 1, dt, ex));
+    for (int64_t k = 0; k < n; ++k) LQ_TRY(efield_link_step(c, k == 0 ? dt / 2.0 : dt, 1, dt, ex, k > 0));
     LQ_TRY(efield_step(c, dt / 2.0, 1));
   } else {
     const double l = c->integ_lambda;
     for (int64_t k = 0; k < n; ++k) {
-      LQ_TRY(efield_link_step(c, k == 0 ? l * dt : 2.0 * l * dt, 1, dt / 2.0, ex));
-      LQ_TRY(efield_link_step(c, (1.0 - 2.0 * l) * dt, 1, dt / 2.0, ex));
+      LQ_TRY(efield_link_step(c, k == 0 ? l * dt : 2.0 * l * dt, 1, dt / 2.0, ex, k > 0));
+      LQ_TRY(efield_link_step(c, (1.0 - 2.0 * l) * dt, 1, dt / 2.0, ex, true));
     }
     LQ_TRY(efield_step(c, l * dt, 1));
   }
@@ -1041,11 +1047,21 @@ static int gauss_field(lq_ctx* c) {
 #ifndef LQ_HOST_EMU
   if (c->p2p_on && c->d_push) {
     // compute + halo push in one kernel: boundary sites of G go straight into the neighbours' ghost layers
+    // Successive evaluations alternate between the two Gauss-field buffers.  The ghosts of the buffer written now were
+    // last read (by the projection step) two evaluations ago, and the data barrier of the evaluation in between -- which
+    // this rank has passed -- was reached by every neighbour only after that reader had finished: no "ready" barrier is
+    // needed as long as the previous evaluation also went through this path (g_pp_safe).
+    const bool skip_ready = c->g_pp_safe && c->G2;
+    if (skip_ready) {
+      cx* t = c->G;
+      c->G = c->G2;
+      c->G2 = t;
+    }
     int bi = -1;
     for (int b = 0; b < LQ_P2P_NBUF - 1; ++b)
       if (c->own[b] == c->G) bi = b;
     if (bi < 0) return LQ_E_COMM;
-    LQ_TRY(p2p_barrier(c));
+    if (!skip_ready) LQ_TRY(p2p_barrier(c));
     {
       ProfScope ps(c, LQ_PROF_GAUSS_FIELD);
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussField<DD>{c->g, c->U, c->E, c->G, (const LqPush*)c->d_push + bi}))));
@@ -1054,6 +1070,7 @@ static int gauss_field(lq_ctx* c) {
     c->p2p_exchanges++;
     c->halo_ok[2] = true;
     c->g_valid = true;
+    c->g_pp_safe = true;
     return LQ_OK;
   }
 #endif
@@ -1095,7 +1112,9 @@ int lq_gauss_project_step(lq_ctx* c) {
   if (!(c->flags & LQ_FLAG_GAUSS_FUSED)) {
     ProfScope ps(c, LQ_PROF_GAUSS_STEP);
     LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KGaussProjectStep<DD>{c->g, c->U, c->G, c->E, c->E2}))));
-    for (int hd = 1; hd < c->g.D; ++hd)  // low-ghost links of the split directions: recomputed, not exchanged
+    // low-ghost links of the split directions: recomputed, not exchanged.  (Folding them into the launch above was
+    // measured slower on 4 GPUs, 49.1 vs 42.9 ms per trajectory: the combined functor costs the main path occupancy.)
+    for (int hd = 1; hd < c->g.D; ++hd)
       if (c->g.ghost[hd])
         LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / c->g.ext[hd],
                                        KGaussProjectGhost<DD>{c->g, c->U, c->G, c->E, c->E2, hd}))));
@@ -1107,6 +1126,7 @@ int lq_gauss_project_step(lq_ctx* c) {
     return LQ_OK;
   }
   LQ_TRY(ensure_buf(&c->G2, c->g_bytes(), c));
+  c->g_pp_safe = false;  // this path swaps the two G buffers without a barrier of its own
   {
     // projection step + Gauss field of the projected E in one pass (KGaussIter)
     ProfScope ps(c, LQ_PROF_GAUSS_STEP);
