@@ -761,8 +761,8 @@ static inline cudaError_t lq_tuned_links_aos(cudaStream_t st, const LqGeom& g, c
 // per-block partial sums of the plaquette terms: ceil(vol / 32) blocks x 3 doubles
 static inline lq_i64 lq_tuned_plaquette_blocks(const LqGeom& g) { return (g.vol + 31) / 32; }
 static inline cudaError_t lq_tuned_plaquette(cudaStream_t st, const LqGeom& g, const cx* U, double CA, double* partial) {
-  // register budgets of 168 / 113 / 85 / 68 per thread (2..5 blocks per SM) all run in 0.31-0.39 ms at 32^4: the kernel is
-  // bound by L2 -> SM traffic (24 link matrices per site), not by latency
+  // register budgets of 168 / 113 / 85 / 68 per thread (2..5 blocks per SM) all run in 0.31-0.39 ms at 32^4; ncu: no unit
+  // above half, 43 % of the instructions are site decode + block reduction (profiles/r01zi_plaq4_ncu.txt)
   lq_plaq4_kernel<2><<<(unsigned)lq_tuned_plaquette_blocks(g), 192, 0, st>>>(g, U, CA, partial);
   return cudaGetLastError();
 }
