@@ -34,7 +34,8 @@ enum {
   LQ_E_SIZE = -2,           /* StateInitializationError::IncompatibleSize (state.rs:784-786)             */
   LQ_E_CUDA = -3,           /* any CUDA runtime failure (lq_last_cuda_error has the text)                */
   LQ_E_COMM = -4,           /* halo transport failure                                                    */
-  LQ_E_ODD_EXTENT = -5,     /* checkerboard sweeps need even extents in every direction                  */
+  LQ_E_ODD_EXTENT = -5,     /* sweeps on a DECOMPOSED context need even extents (single-rank contexts sweep odd
+                               lattices in colour classes, see the sweep section)                        */
   LQ_E_GAUSS_DIVERGED = -6, /* StateInitializationError::GaussProjectionError (field.rs:1279-1281)       */
   LQ_E_ZERO_STEPS = -7,     /* MultiIntegrationError::ZeroIntegration (state.rs:331-333, 480-482)        */
   LQ_E_NOSNAPSHOT = -8,
@@ -154,7 +155,10 @@ int lq_gauss_sum_div(lq_ctx*, double* out);        /* field.rs:1199-1220 */
 int lq_gauss_project_step(lq_ctx*);                /* field.rs:1301-1337 */
 int lq_gauss_project(lq_ctx*, int64_t max_steps, int64_t* steps_out);  /* field.rs:1265-1294 */
 
-/* ---- local-update sweeps (even/odd checkerboard; visit order: for dir, for parity) -------------------------- */
+/* ---- local-update sweeps (even/odd checkerboard; visit order: for dir, for parity) --------------------------
+ * Lattices with odd extents (accepted by the reference's sequential sweeps, lattice.rs:190-201) are swept in the colour
+ * classes (boundary mask, parity): for dir, for mask, for parity -- bit d of the mask set iff ext[d] is odd and
+ * x_d = ext[d] - 1 -- because two colours do not decouple a periodic ring of odd length. */
 int lq_sweep_heatbath(lq_ctx*, uint64_t seed, uint64_t counter, double coupling_scale); /* heat_bath.rs:73-123 */
 int lq_sweep_overrelax(lq_ctx*, int kind);                                              /* overrelaxation.rs    */
 int lq_sweep_metropolis(lq_ctx*, uint64_t seed, uint64_t counter, double spread, int n_update, int64_t* n_accept,

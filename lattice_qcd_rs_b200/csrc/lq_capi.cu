@@ -106,6 +106,7 @@ struct lq_ctx {
   bool decomposed;
   int nproc[LQ_MAXD];
   bool even_extents;
+  int odd_mask;  // bit d: ext[d] is odd (sweeps then use the colour classes of lq_site_class); 0 when all are even
   cx *U, *U2, *E, *E2, *G, *G2;
   cx *snapU, *snapE;
   int64_t snap_t;
@@ -414,6 +415,7 @@ static int ctx_create_common(lq_ctx** out, int device, int D, const int64_t* gex
     c->nproc[d] = (nproc && d < D) ? nproc[d] : 1;
     if (c->nproc[d] > 1) c->decomposed = true;
     if (d < D && (g.gext[d] & 1 || g.ext[d] & 1)) c->even_extents = false;
+    if (d < D && (g.ext[d] & 1)) c->odd_mask |= 1 << d;
   }
   int rc = LQ_OK;
 #ifndef LQ_HOST_EMU
@@ -444,7 +446,7 @@ const char* lq_strerror(int code) {
     case LQ_E_SIZE: return "incompatible size (StateInitializationError::IncompatibleSize)";
     case LQ_E_CUDA: return "CUDA error";
     case LQ_E_COMM: return "halo / all-reduce transport error (is lq_set_comm registered?)";
-    case LQ_E_ODD_EXTENT: return "checkerboard sweeps need even extents";
+    case LQ_E_ODD_EXTENT: return "sweeps on a decomposed context need even extents";
     case LQ_E_GAUSS_DIVERGED: return "Gauss projection did not converge (GaussProjectionError)";
     case LQ_E_ZERO_STEPS: return "zero integration steps (MultiIntegrationError::ZeroIntegration)";
     case LQ_E_NOSNAPSHOT: return "no snapshot to restore";
@@ -1172,65 +1174,75 @@ int lq_gauss_project(lq_ctx* c, int64_t max_steps, int64_t* steps_out) {
 }
 
 // ---------------------------------------------------------------------------------------------- sweeps
+// Sub-steps of a sweep: for dir, [for colour class of an odd lattice,] for parity.  Even extents: two colours, vol/2
+// sites per launch.  Odd extents (single-rank contexts only): classes (boundary mask, parity), every launch scans the
+// whole volume (lq_site_class).
+static bool sweep_supported(const lq_ctx* c) { return c->even_extents || !c->decomposed; }
+#define LQ_SWEEP_LOOP(c, BODY)                                             \
+  for (int d = 0; d < (c)->g.D; ++d)                                      \
+    for (int cm = 0; cm <= (c)->odd_mask; ++cm) {                         \
+      if (cm & ~(c)->odd_mask) continue;                                  \
+      for (int p = 0; p < 2; ++p) {                                       \
+        const int om = (c)->odd_mask;                                     \
+        const lq_i64 nitems = om ? (c)->g.vol : (c)->g.vol / 2;           \
+        BODY                                                              \
+      }                                                                   \
+    }
 int lq_sweep_heatbath(lq_ctx* c, uint64_t seed, uint64_t counter, double coupling_scale) {
   if (!c) return LQ_E_BADARG;
-  if (!c->even_extents) return LQ_E_ODD_EXTENT;
+  if (!sweep_supported(c)) return LQ_E_ODD_EXTENT;
   LQ_GUARD(c);
-  for (int d = 0; d < c->g.D; ++d)
-    for (int p = 0; p < 2; ++p) {
-      LQ_TRY(ensure_halo(c, 0));
-      ProfScope ps(c, LQ_PROF_HEATBATH);
+  LQ_SWEEP_LOOP(c, {
+    LQ_TRY(ensure_halo(c, 0));
+    ProfScope ps(c, LQ_PROF_HEATBATH);
 #ifdef LQ_TUNED
-      if (lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
-        LQ_CHECK(lq_tuned_sweep(c->stream, c->g, c->U, 0, d, p, c->flags, 0, c->beta * coupling_scale, seed, counter));
-        c->launches++;
-      } else
+    if (!om && lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+      LQ_CHECK(lq_tuned_sweep(c->stream, c->g, c->U, 0, d, p, c->flags, 0, c->beta * coupling_scale, seed, counter));
+      c->launches++;
+    } else
 #endif
-      LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2,
-                                     KHeatBath<DD>{c->g, c->U, d, p, c->flags, c->beta * coupling_scale, seed, counter}))));
-      c->halo_ok[0] = false;
-      c->g_valid = false;
-    }
+    LQ_DISPATCH(c, LQ_TRY((launch(c, nitems, KHeatBath<DD>{c->g, c->U, d, p, c->flags, c->beta * coupling_scale, seed,
+                                                          counter, om, cm}))));
+    c->halo_ok[0] = false;
+    c->g_valid = false;
+  })
   return LQ_OK;
 }
 int lq_sweep_overrelax(lq_ctx* c, int kind) {
   if (!c || (kind != LQ_OR_ROTATION && kind != LQ_OR_REVERSE && kind != LQ_OR_SU2_SUBGROUPS)) return LQ_E_BADARG;
-  if (!c->even_extents) return LQ_E_ODD_EXTENT;
+  if (!sweep_supported(c)) return LQ_E_ODD_EXTENT;
   LQ_GUARD(c);
-  for (int d = 0; d < c->g.D; ++d)
-    for (int p = 0; p < 2; ++p) {
-      LQ_TRY(ensure_halo(c, 0));
-      ProfScope ps(c, LQ_PROF_OVERRELAX);
+  LQ_SWEEP_LOOP(c, {
+    LQ_TRY(ensure_halo(c, 0));
+    ProfScope ps(c, LQ_PROF_OVERRELAX);
 #ifdef LQ_TUNED
-      if (lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
-        LQ_CHECK(lq_tuned_sweep(c->stream, c->g, c->U, 1, d, p, c->flags, kind, 0.0, 0, 0));
-        c->launches++;
-      } else
+    if (!om && lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+      LQ_CHECK(lq_tuned_sweep(c->stream, c->g, c->U, 1, d, p, c->flags, kind, 0.0, 0, 0));
+      c->launches++;
+    } else
 #endif
-      LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol / 2, KOverrelax<DD>{c->g, c->U, d, p, kind}))));
-      c->halo_ok[0] = false;
-      c->g_valid = false;
-    }
+    LQ_DISPATCH(c, LQ_TRY((launch(c, nitems, KOverrelax<DD>{c->g, c->U, d, p, kind, om, cm}))));
+    c->halo_ok[0] = false;
+    c->g_valid = false;
+  })
   return LQ_OK;
 }
 int lq_sweep_metropolis(lq_ctx* c, uint64_t seed, uint64_t counter, double spread, int n_update, int64_t* n_accept,
                         double* sum_prob) {
   if (!c || n_update < 1 || !(spread > 0.0 && spread < 1.0)) return LQ_E_BADARG;  // metropolis_hastings_sweep.rs:73-80
-  if (!c->even_extents) return LQ_E_ODD_EXTENT;
+  if (!sweep_supported(c)) return LQ_E_ODD_EXTENT;
   LQ_GUARD(c);
   double acc[2] = {0.0, 0.0};
-  for (int d = 0; d < c->g.D; ++d)
-    for (int p = 0; p < 2; ++p) {
-      LQ_TRY(ensure_halo(c, 0));
-      ProfScope ps(c, LQ_PROF_METROPOLIS);
-      LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol / 2,
-                                     KMetropolis<DD>{c->g, c->U, d, p, c->flags, n_update, c->beta, c->CA, spread, seed,
-                                                     counter}))));
-      acc[0] += c->h_result[0];
-      acc[1] += c->h_result[1];
-      c->halo_ok[0] = false;
-      c->g_valid = false;
-    }
+  LQ_SWEEP_LOOP(c, {
+    LQ_TRY(ensure_halo(c, 0));
+    ProfScope ps(c, LQ_PROF_METROPOLIS);
+    LQ_DISPATCH(c, LQ_TRY((reduce(c, nitems, KMetropolis<DD>{c->g, c->U, d, p, c->flags, n_update, c->beta, c->CA, spread,
+                                                            seed, counter, om, cm}))));
+    acc[0] += c->h_result[0];
+    acc[1] += c->h_result[1];
+    c->halo_ok[0] = false;
+    c->g_valid = false;
+  })
   LQ_TRY(global_sum(c, acc, 2));
   if (n_accept) *n_accept = (int64_t)(acc[0] + 0.5);
   if (sum_prob) *sum_prob = acc[1];

@@ -161,6 +161,29 @@ LQ_HD Site<D> lq_site_eo(const LqGeom& g, lq_i64 n, int parity) {
   st.s += st.x[0];
   return st;
 }
+// Site of one sweep sub-step.  Even extents (odd_mask == 0): `n` enumerates the vol/2 sites of colour `parity`.
+// Odd extents (non-decomposed contexts; the reference's sequential sweeps accept any N >= 2): two colours are not
+// enough on a periodic ring of odd length, so the colour of a site is (boundary mask, parity) with bit d of the mask set
+// iff ext[d] is odd and x_d = ext[d] - 1.  Neighbours x, x + nu always differ: in parity away from the wrap (and for
+// even ext[nu]), in bit nu of the mask at x_nu = N-2 -> N-1 and N-1 -> 0.  Here `n` enumerates ALL sites and the call
+// returns false for the ones outside the class (odd lattices are small: the scan is cheaper than a second enumeration).
+template <int D>
+LQ_HD bool lq_site_class(const LqGeom& g, lq_i64 n, int parity, int odd_mask, int cmask, Site<D>& st) {
+  if (odd_mask == 0) {
+    st = lq_site_eo<D>(g, n, parity);
+    return true;
+  }
+  if (n >= g.vol) return false;
+  st = lq_site<D>(g, n);
+  int m = 0, ps = 0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const int xd = st.x[d] - g.ghost[d];
+    ps += xd;
+    if (((odd_mask >> d) & 1) && xd == g.ext[d] - 1) m |= 1 << d;
+  }
+  return m == cmask && (ps & 1) == parity;
+}
 // add_point_direction (lattice.rs:303-323): one step with periodic wrap.  In a ghosted direction interior
 // sites never wrap (the neighbour is the ghost layer).
 template <int D>

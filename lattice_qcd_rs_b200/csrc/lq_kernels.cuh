@@ -708,8 +708,10 @@ struct KHeatBath {  // HeatBathSweep, heat_bath.rs:73-123
   int dir, parity, flags;
   double coupling;  // beta * coupling_scale
   uint64_t seed, counter;
+  int odd_mask, cmask;  // colour classes of lattices with odd extents (lq_site_class); 0, 0 otherwise
   LQ_HD void operator()(lq_i64 n) const {
-    Site<D> x = lq_site_eo<D>(g, n, parity);
+    Site<D> x;
+    if (!lq_site_class<D>(g, n, parity, odd_mask, cmask, x)) return;
     lq_i64 p = lq_slot<D>(g, x);
     M3 a = lq_staple_sum<D>(U, g, x, dir);
     M3 u = lq_load_link_rw(U, g, dir, p);
@@ -722,8 +724,10 @@ struct KOverrelax {  // OverrelaxationSweep{Rotation,Reverse}, overrelaxation.rs
   LqGeom g;
   cx* U;
   int dir, parity, kind;
+  int odd_mask, cmask;
   LQ_HD void operator()(lq_i64 n) const {
-    Site<D> x = lq_site_eo<D>(g, n, parity);
+    Site<D> x;
+    if (!lq_site_class<D>(g, n, parity, odd_mask, cmask, x)) return;
     lq_i64 p = lq_slot<D>(g, x);
     M3 a = lq_staple_sum<D>(U, g, x, dir);
     M3 u = lq_load_link_rw(U, g, dir, p);
@@ -738,8 +742,10 @@ struct KMetropolis {  // MetropolisHastingsSweep, metropolis_hastings_sweep.rs:1
   int dir, parity, flags, n_update;
   double beta, CA, spread;
   uint64_t seed, counter;
+  int odd_mask, cmask;
   LQ_HD void operator()(lq_i64 n, double* v) const {
-    Site<D> x = lq_site_eo<D>(g, n, parity);
+    Site<D> x;
+    if (!lq_site_class<D>(g, n, parity, odd_mask, cmask, x)) return;
     lq_i64 p = lq_slot<D>(g, x);
     M3 old = lq_load_link_rw(U, g, dir, p);
     LqStream rng(seed, counter, (uint64_t)(lq_global_index<D>(g, x) * D + dir));

@@ -864,15 +864,29 @@ inline int site_parity(const Lattice& L, int64_t x) {
   for (int k = 0; k < L.D; ++k) p += (x / L.stride[k]) % L.ext[k];
   return (int)(p & 1);
 }
+// Lattices with odd extents: two colours do not decouple a periodic ring of odd length; the CUDA path uses the classes
+// (boundary mask, parity), bit k of the mask set iff ext[k] is odd and x_k = ext[k] - 1 (lq_site_class).
+inline int site_boundary_mask(const Lattice& L, int64_t x) {
+  int m = 0;
+  for (int k = 0; k < L.D; ++k)
+    if ((L.ext[k] & 1) && (x / L.stride[k]) % L.ext[k] == L.ext[k] - 1) m |= 1 << k;
+  return m;
+}
 template <class F>
 inline void for_each_link(const Lattice& L, int order, F f) {
   if (order == SEQUENTIAL) {
     for (int64_t l = 0; l < L.nl(); ++l) f(l / L.D, (int)(l % L.D));
   } else {
+    int om = 0;
+    for (int k = 0; k < L.D; ++k)
+      if (L.ext[k] & 1) om |= 1 << k;
     for (int d = 0; d < L.D; ++d)
-      for (int p = 0; p < 2; ++p)
-        for (int64_t x = 0; x < L.ns; ++x)
-          if (site_parity(L, x) == p) f(x, d);
+      for (int cm = 0; cm <= om; ++cm) {
+        if (cm & ~om) continue;
+        for (int p = 0; p < 2; ++p)
+          for (int64_t x = 0; x < L.ns; ++x)
+            if (site_parity(L, x) == p && site_boundary_mask(L, x) == cm) f(x, d);
+      }
   }
 }
 // rng mode: per_link = true  -> Stream(seed, counter, global link index) per link (CUDA-comparable)

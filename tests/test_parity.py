@@ -78,11 +78,9 @@ def test_errors(backend):
     with pytest.raises(LqError) as e:
         c.restore()
     assert e.value.name == "LQ_E_NOSNAPSHOT"
-    odd = backend(4, [5, 4, 4, 4])
+    odd = backend(4, [5, 4, 4, 4])  # odd extents are fine on a single rank (colour classes, test_sweeps_on_odd_extents)
     odd.links_set_cold()
-    with pytest.raises(LqError) as e:
-        odd.sweep_heatbath(1, 0)
-    assert e.value.name == "LQ_E_ODD_EXTENT"
+    odd.sweep_heatbath(1, 0)
     with pytest.raises(LqError):  # spread must be in (0,1): metropolis_hastings_sweep.rs:73-80
         c.sweep_metropolis(1, 0, spread=1.5)
 
@@ -482,3 +480,29 @@ def test_integrator_options(backend, D, ext):
         c.set_integrator(INTEGRATOR_OMELYAN, 0.7, True)
     with pytest.raises(LqError):
         c.set_integrator(5, 0.2, True)
+
+
+@pytest.mark.parametrize("D,ext", [(4, [5, 4, 3, 4]), (3, [3, 5, 7]), (2, [5, 6]), (4, [3, 3, 3, 3])])
+def test_sweeps_on_odd_extents(backend, D, ext):
+    """The reference's sequential sweeps accept any N >= 2 (lattice.rs:190-201).  On a periodic ring of odd length two
+    colours do not decouple the links of a sub-step, so lattices with odd extents are swept in the colour classes
+    (boundary mask, parity) of lq_site_class -- restated in the oracle's checkerboard order; element-wise parity as for
+    even lattices, and every link is visited exactly once per sweep."""
+    o = Oracle(D, ext, a=1.0, beta=6.0)
+    c = backend(D, ext, a=1.0, beta=6.0)
+    U = hot(o)
+    c.links_upload(U)
+    c.sweep_heatbath(SEED_RNG, 11)
+    got = c.links_download()
+    assert rel(got, o.sweep_heatbath(U, SEED_RNG, 11, order=1, per_link=True)) <= 1e-9
+    assert np.all(np.abs(got - U).reshape(o.nl, 18).max(axis=1) > 1e-6)  # no link left out
+    for kind in (0, 1, 2):
+        c.links_upload(U)
+        h0 = c.hamiltonian_links()
+        c.sweep_overrelax(kind)
+        assert rel(c.links_download(), o.sweep_overrelax(U, kind, order=1)) <= 1e-9
+        assert abs(c.hamiltonian_links() - h0) <= 1e-10 * abs(h0)  # microcanonical only if no two links interfered
+    c.links_upload(U)
+    na, sp = c.sweep_metropolis(SEED_RNG, 13, spread=0.1, n_update=2)
+    Uo, nao, spo = o.sweep_metropolis(U, SEED_RNG, 13, n_update=2, spread=0.1, order=1, per_link=True)
+    assert na == nao and abs(sp - spo) <= 1e-9 * spo and rel(c.links_download(), Uo) <= 1e-9
