@@ -1233,6 +1233,32 @@ int lq_sweep_metropolis(lq_ctx* c, uint64_t seed, uint64_t counter, double sprea
   if (!sweep_supported(c)) return LQ_E_ODD_EXTENT;
   LQ_GUARD(c);
   double acc[2] = {0.0, 0.0};
+#if defined(LQ_HAVE_TUNED) && !defined(LQ_HOST_EMU)
+  if (!c->odd_mask && lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+    // tuned D = 4 sub-steps; their per-block statistics are reduced ONCE per sweep (one host synchronisation, one
+    // all-reduce on decomposed contexts) instead of once per sub-step
+    const lq_i64 nb = lq_tuned_metropolis_blocks(c->g);
+    LQ_TRY(reduce_reserve(c, nb * 8, 2));
+    int sub = 0;
+    for (int d = 0; d < 4; ++d)
+      for (int p = 0; p < 2; ++p, ++sub) {
+        LQ_TRY(ensure_halo(c, 0));
+        ProfScope ps(c, LQ_PROF_METROPOLIS);
+        LQ_CHECK(lq_tuned_metropolis(c->stream, c->g, c->U, d, p, c->flags, n_update, c->beta, c->CA, spread, seed, counter,
+                                     c->d_partial + (size_t)sub * nb * 2));
+        c->launches++;
+        c->halo_ok[0] = false;
+        c->g_valid = false;
+      }
+    LQ_TRY(reduce_finish<2>(c, nb * 8));
+    acc[0] = c->h_result[0];
+    acc[1] = c->h_result[1];
+    LQ_TRY(global_sum(c, acc, 2));
+    if (n_accept) *n_accept = (int64_t)(acc[0] + 0.5);
+    if (sum_prob) *sum_prob = acc[1];
+    return LQ_OK;
+  }
+#endif
   LQ_SWEEP_LOOP(c, {
     LQ_TRY(ensure_halo(c, 0));
     ProfScope ps(c, LQ_PROF_METROPOLIS);

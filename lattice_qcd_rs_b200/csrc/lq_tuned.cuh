@@ -565,6 +565,94 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Metropolis sub-step (one direction, one colour), D = 4: MetropolisHastingsSweep (metropolis_hastings_sweep.rs:126-174)
+// with the lean addressing of lq_sweep4_kernel and the same arithmetic as KMetropolis (staple order nu ascending, up
+// then down; proposal draws, then the accept draw, from the link's Philox stream).  The block's (#accepted, sum of
+// acceptance probabilities) go to partial[2 * blockIdx]: the eight sub-steps of a sweep write eight consecutive
+// segments and ONE final reduction (and one host synchronisation) serves the whole sweep.
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_metro4_kernel(LqGeom g, cx* __restrict__ U, int mu, int parity, int flags, int n_update, double beta, double CA,
+                     double spread, unsigned long long seed, unsigned long long counter, double* __restrict__ partial) {
+  const int n = blockIdx.x * BLOCK + threadIdx.x;
+  double v0 = 0.0, v1 = 0.0;
+  if (n < (int)(g.vol >> 1)) {
+    const int e0 = g.ext[0], ne0 = g.ne0, h0 = e0 >> 1;
+    int row = n / h0;
+    const int k = n - row * h0;
+    int q = row / g.ext[1];
+    const int i1 = row - q * g.ext[1];
+    row = q;
+    q = row / g.ext[2];
+    const int i2 = row - q * g.ext[2];
+    const int i3 = q;
+    const int x0 = 2 * k + ((parity + i1 + g.goff[1] + i2 + g.goff[2] + i3 + g.goff[3] + g.goff[0]) & 1);
+    const int x1 = i1 + g.ghost[1], x2 = i2 + g.ghost[2], x3 = i3 + g.ghost[3];
+    const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
+    const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
+    const int p = x1 * s1 + x2 * s2 + x3 * s3 + sl0;
+    const int x0p = x0 + 1 < e0 ? x0 + 1 : 0, x0m = x0 > 0 ? x0 - 1 : e0 - 1;
+    const int up0 = (x0p & 1) * ne0 + (x0p >> 1) - sl0, dn0 = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
+    const int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
+    const int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
+    const int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
+    const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
+    M3 acc = m3_zero();
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+      const int nu = j + (j >= mu ? 1 : 0);  // ascending, own direction skipped
+      const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
+      {
+        M3 a = lq_ld36(U, pm, nu);
+        M3 b = lq_ld36(U, p + upn, mu);
+        M3 t = m3_mul_nd(a, b);
+        M3 c = lq_ld36(U, p, nu);
+        m3_fma_nd(acc, t, c);
+      }
+      {
+        M3 a = lq_ld36(U, p + dnn, mu);
+        M3 b = lq_ld36(U, pm + dnn, nu);
+        M3 t = m3_mul_nn(a, b);
+        M3 c = lq_ld36(U, p + dnn, nu);
+        m3_fma_dn(acc, t, c);
+      }
+    }
+    cx* own = U + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
+    M3 old;
+#pragma unroll
+    for (int kk = 0; kk < 9; ++kk) old.e[kk] = own[kk * 32];
+    const lq_i64 gi = (lq_i64)(x0 + g.goff[0]) * g.gstride[0] + (lq_i64)(i1 + g.goff[1]) * g.gstride[1] +
+                      (lq_i64)(i2 + g.goff[2]) * g.gstride[2] + (lq_i64)(i3 + g.goff[3]) * g.gstride[3];
+    LqStream rng(seed, counter, (uint64_t)(gi * 4 + mu));
+    const M3 prop = lq_metropolis_proposal(old, n_update, spread, rng, flags);
+    const double proba = fmax(fmin(exp(-lq_delta_s(acc, prop, old, beta, CA)), 1.0), 0.0);
+    v1 = proba;
+    if (rng.bernoulli(proba)) {
+      v0 = 1.0;
+#pragma unroll
+      for (int kk = 0; kk < 9; ++kk) own[kk * 32] = prop.e[kk];
+    }
+  }
+  __shared__ double sm[2][BLOCK / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v0 += __shfl_down_sync(0xffffffffu, v0, o);
+    v1 += __shfl_down_sync(0xffffffffu, v1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sm[0][threadIdx.x >> 5] = v0;
+    sm[1][threadIdx.x >> 5] = v1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < BLOCK / 32; ++w) x += sm[threadIdx.x][w];
+    partial[(lq_i64)blockIdx.x * 2 + threadIdx.x] = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Plaquette reduction, D = 4 (average_trace_plaquette field.rs:775-804, hamiltonian_links state.rs:821-849): the terms
 // of KPlaquette with the lean addressing of V4.  One thread per (site, plane i < j), a warp = 32 consecutive site slots
 // of one plane, a block = 32 sites x 6 planes.  Per-block partial sums (sum Re Tr P, sum Im Tr P, sum (1 - Re Tr P/CA))
@@ -756,6 +844,14 @@ static inline cudaError_t lq_tuned_links_aos(cudaStream_t st, const LqGeom& g, c
     if (e != cudaSuccess) return e;
     lq_aos4_tma_kernel<0><<<rows, 128, smem, st>>>(g, U, aos);
   }
+  return cudaGetLastError();
+}
+static inline lq_i64 lq_tuned_metropolis_blocks(const LqGeom& g) { return (g.vol / 2 + 127) / 128; }
+static inline cudaError_t lq_tuned_metropolis(cudaStream_t st, const LqGeom& g, cx* U, int mu, int parity, int flags,
+                                              int n_update, double beta, double CA, double spread, unsigned long long seed,
+                                              unsigned long long counter, double* partial) {
+  lq_metro4_kernel<128, 3><<<(unsigned)lq_tuned_metropolis_blocks(g), 128, 0, st>>>(g, U, mu, parity, flags, n_update, beta,
+                                                                                  CA, spread, seed, counter, partial);
   return cudaGetLastError();
 }
 // per-block partial sums of the plaquette terms: ceil(vol / 32) blocks x 3 doubles
