@@ -80,6 +80,18 @@ struct LqStream {
   }
 };
 
+// cos(2 pi x): on the device cospi has an exact argument reduction (no slow path); the host build keeps libm's cos
+#if defined(__CUDA_ARCH__)
+#define LQ_COS_2PI(x) cospi(2.0 * (x))
+#else
+#define LQ_COS_2PI(x) cos(2.0 * LQ_PI * (x))
+#endif
+// 1/sqrt(x): rsqrt is a CUDA function (also callable from host code under nvcc); the g++ host build has none
+#ifdef LQ_HOST_EMU
+#define LQ_RSQRT(x) (1.0 / sqrt(x))
+#else
+#define LQ_RSQRT(x) rsqrt(x)
+#endif
 #define LQ_KP_MAX_ITER 10000 /* the reference loops forever on NaN parameters; cap and return x0 = 1 */
 
 // ---------------------------------------------------------------------------------------------- 2x2
@@ -234,7 +246,7 @@ LQ_HD double lq_heat_bath_norm(double param_exp, LqStream& rng) {
     double r0 = rng.open_closed01();
     double r1 = rng.open_closed01();
     double r2 = rng.open_closed01();
-    double c = cos(2.0 * LQ_PI * r1);
+    double c = LQ_COS_2PI(r1);
     double l2 = -(log(r0) + c * c * log(r2)) * inv2a;
     if (r * r <= 1.0 - l2) return 1.0 - 2.0 * l2;
   }
@@ -244,17 +256,18 @@ LQ_HD double lq_heat_bath_norm(double param_exp, LqStream& rng) {
 // LQ_FLAG_UNIFORM_DIRECTION cube samples outside the unit ball are rejected => uniform on the sphere)
 LQ_HD M2 lq_heat_bath_matrix(double param_exp, LqStream& rng, int flags) {
   double x0 = lq_heat_bath_norm(param_exp, rng);
-  double xu[3], n;
+  double xu[3], n2;
   int guard = 0;
   do {
     xu[0] = rng.uniform_pm1();
     xu[1] = rng.uniform_pm1();
     xu[2] = rng.uniform_pm1();
-    n = sqrt(xu[0] * xu[0] + xu[1] * xu[1] + xu[2] * xu[2]);
-  } while ((n <= LQ_EPS || ((flags & 16) && n > 1.0)) && ++guard < LQ_KP_MAX_ITER);  // 16: LQ_FLAG_UNIFORM_DIRECTION
-  // one reciprocal instead of three divisions (the reference divides each component, distribution.rs:214: the results
-  // differ by an ulp at most, far inside the 1e-9 tolerance of the stochastic paths; 36 divisions per link otherwise)
-  const double sc = sqrt(1.0 - x0 * x0) * (1.0 / n);
+    n2 = xu[0] * xu[0] + xu[1] * xu[1] + xu[2] * xu[2];  // the tests of distribution.rs:209-213 on the squared length
+  } while ((n2 <= LQ_EPS * LQ_EPS || ((flags & 16) && n2 > 1.0)) && ++guard < LQ_KP_MAX_ITER);  // 16: LQ_FLAG_UNIFORM_DIRECTION
+  // x = xu / |xu| * sqrt(1 - x0^2) with one reciprocal square root instead of a square root and three divisions (the
+  // reference divides each component, distribution.rs:214: the results differ by an ulp or two, far inside the 1e-9
+  // tolerance of the stochastic paths)
+  const double sc = sqrt(1.0 - x0 * x0) * LQ_RSQRT(n2);
   double x[3] = {xu[0] * sc, xu[1] * sc, xu[2] * sc};
   return lq_matrix_from_vec(x0, x, flags);
 }
