@@ -398,13 +398,16 @@ LQ_HD void lq_svd3(const M3& a, M3& u, M3& v) {
           aqq += cnorm2(w.e[3 * k + q]);
           apq = cadd(apq, cmul(cconj(w.e[3 * k + p]), w.e[3 * k + q]));
         }
-        double gg = sqrt(cnorm2(apq));
-        if (gg <= 1e-300 || gg <= 1e-17 * sqrt(app * aqq)) continue;
-        off = fmax(off, gg / sqrt(app * aqq));
-        cx ph = cmk(apq.x / gg, apq.y / gg);
-        double zeta = (aqq - app) / (2.0 * gg);
+        // the rotation's scalars from reciprocals (one division-class operation each instead of five divisions and
+        // four square roots; the decomposition converges to the same factors, the iterates differ in the last bits)
+        const double g2 = cnorm2(apq), pq = app * aqq;
+        if (g2 <= 1e-300 * 1e-300 || g2 <= 1e-34 * pq) continue;
+        const double rg = LQ_RSQRT(g2), gg = g2 * rg;  // gg = |apq|
+        off = fmax(off, gg * LQ_RSQRT(pq));
+        cx ph = cmk(apq.x * rg, apq.y * rg);
+        double zeta = (aqq - app) * (0.5 * rg);
         double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        double c = LQ_RSQRT(1.0 + t * t), sn = c * t;
         cx phc_sn = cscale(cconj(ph), sn), ph_sn = cscale(ph, sn);
         for (int k = 0; k < 3; ++k) {
           cx wp = w.e[3 * k + p], wq = w.e[3 * k + q];
@@ -419,11 +422,11 @@ LQ_HD void lq_svd3(const M3& a, M3& u, M3& v) {
   }
   u = m3_zero();
   for (int j = 0; j < 3; ++j) {
-    double n = 0.0;
-    for (int k = 0; k < 3; ++k) n += cnorm2(w.e[3 * k + j]);
-    n = sqrt(n);
+    double n2 = 0.0;
+    for (int k = 0; k < 3; ++k) n2 += cnorm2(w.e[3 * k + j]);
+    const double rn = n2 > 0.0 ? LQ_RSQRT(n2) : 0.0;
     for (int k = 0; k < 3; ++k)
-      u.e[3 * k + j] = (n > 0.0) ? cmk(w.e[3 * k + j].x / n, w.e[3 * k + j].y / n) : cmk(k == j ? 1.0 : 0.0, 0.0);
+      u.e[3 * k + j] = (n2 > 0.0) ? cmk(w.e[3 * k + j].x * rn, w.e[3 * k + j].y * rn) : cmk(k == j ? 1.0 : 0.0, 0.0);
   }
 }
 // su3::reverse, su3.rs:705-714: negate the off-diagonal entries

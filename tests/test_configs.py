@@ -132,7 +132,7 @@ def test_config3_full_size_properties():
     c.reunitarize()
     V = c.links_download()
     c.reunitarize()
-    assert rel(c.links_download(), V) <= 1e-14
+    assert rel(c.links_download(), V) <= 1e-13  # max over 75 M entries of a second Gram-Schmidt pass: a few dozen ulp
     M = to_c(V[:: 4099])
     assert np.abs(M @ np.conj(np.swapaxes(M, 1, 2)) - np.eye(3)).max() <= 1e-12
     assert np.abs(np.linalg.det(M) - 1.0).max() <= 1e-12
