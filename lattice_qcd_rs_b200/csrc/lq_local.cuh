@@ -133,10 +133,12 @@ LQ_HD M2 lq_random_su2_close_to_unity(double spread, LqStream& rng, int flags) {
   r[0] = rng.uniform_pm1();
   r[1] = rng.uniform_pm1();
   r[2] = rng.uniform_pm1();
-  double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  // try_normalize(eps) of su2.rs:88 with one reciprocal square root for the three components (<= 2 ulp from dividing)
+  const double n2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  const double sc = (n2 > LQ_EPS * LQ_EPS ? LQ_RSQRT(n2) : 1.0) * spread;
   double x[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) x[k] = (n > LQ_EPS ? r[k] / n : r[k]) * spread;
+  for (int k = 0; k < 3; ++k) x[k] = r[k] * sc;
   double x0u = sqrt(1.0 - (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]));
   double x0 = rng.bernoulli(0.5) ? x0u : -x0u;
   return lq_matrix_from_vec(x0, x, flags);
@@ -360,11 +362,47 @@ struct LqOverrelaxSu2Rule {
     return m2_mul(v, v);
   }
 };
+// orthonormalize_matrix (su3.rs:279-303) for the proposals: the arithmetic of lq_orthonormalize with each column scaled by
+// one reciprocal square root instead of six divisions (the deterministic reprojection keeps the literal form)
+LQ_HD M3 lq_orthonormalize_rs(const M3& a) {
+  cx v1[3] = {a.e[0], a.e[3], a.e[6]};
+  cx v2[3] = {a.e[1], a.e[4], a.e[7]};
+  const double q1 = cnorm2(v1[0]) + cnorm2(v1[1]) + cnorm2(v1[2]);
+  if (q1 > LQ_EPS * LQ_EPS) {
+    const double s1 = LQ_RSQRT(q1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v1[k] = cmk(v1[k].x * s1, v1[k].y * s1);
+  }
+  cx d = cmk(0.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cfma_ca(d, v1[k], v2[k]);
+  cx w[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w[k] = csub(v2[k], cmul(v1[k], d));
+  const double q2 = cnorm2(w[0]) + cnorm2(w[1]) + cnorm2(w[2]);
+  if (q2 > LQ_EPS * LQ_EPS) {
+    const double s2 = LQ_RSQRT(q2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[k] = cmk(w[k].x * s2, w[k].y * s2);
+  }
+  cx a1[3] = {cconj(v1[0]), cconj(v1[1]), cconj(v1[2])};
+  cx b1[3] = {cconj(w[0]), cconj(w[1]), cconj(w[2])};
+  cx cr[3] = {csub(cmul(a1[1], b1[2]), cmul(a1[2], b1[1])), csub(cmul(a1[2], b1[0]), cmul(a1[0], b1[2])),
+              csub(cmul(a1[0], b1[1]), cmul(a1[1], b1[0]))};
+  M3 r;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r.e[3 * k + 0] = v1[k];
+    r.e[3 * k + 1] = w[k];
+    r.e[3 * k + 2] = cr[k];
+  }
+  return r;
+}
 // MetropolisHastingsSweep::potential_modif, metropolis_hastings_sweep.rs:126-143
 LQ_HD M3 lq_metropolis_proposal(const M3& old_link, int n_update, double spread, LqStream& rng, int flags) {
   M3 nl = old_link;
   for (int k = 0; k < n_update; ++k) {
-    M3 rm = lq_orthonormalize(lq_random_su3_close_to_unity(spread, rng, flags));
+    M3 rm = lq_orthonormalize_rs(lq_random_su3_close_to_unity(spread, rng, flags));
     nl = m3_mul_nn(rm, nl);
   }
   return nl;
