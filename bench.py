@@ -320,8 +320,8 @@ def run_ours(args):
                                  "pass, 1376 B/site; FP64 co-limited: 32 matrix products/site)", 1376 * ns_local, n_gs, ms_gs),
                            _roof("KGaussField<4> (976 B/site)", 976 * ns_local, n_gf, ms_gf)]
     else:
-        gauss_rooflines = [_roof("KGaussField<4> (976 B/site)", 976 * ns_local, n_gf, ms_gf),
-                           _roof("KGaussProjectStep<4> (308 B/link)", 308 * nl_local, n_gs, ms_gs)]
+        gauss_rooflines = [_roof("lq_gfield4_kernel (EField::gauss, 976 B/site)", 976 * ns_local, n_gf, ms_gf),
+                           _roof("lq_gstep4_kernel (project_to_gauss_step, 308 B/link)", 308 * nl_local, n_gs, ms_gs)]
     line = {
         "metric": "HMC link-updates/sec at 32^4 f64", "value": value, "unit": "link-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

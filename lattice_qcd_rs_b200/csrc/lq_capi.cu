@@ -1066,6 +1066,12 @@ static int gauss_field(lq_ctx* c) {
     if (!skip_ready) LQ_TRY(p2p_barrier(c));
     {
       ProfScope ps(c, LQ_PROF_GAUSS_FIELD);
+#ifdef LQ_HAVE_TUNED
+      if (lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+        LQ_CHECK(lq_tuned_gauss_field(c->stream, c->g, c->U, c->E, c->G, (const LqPush*)c->d_push + bi));
+        c->launches++;
+      } else
+#endif
       LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussField<DD>{c->g, c->U, c->E, c->G, (const LqPush*)c->d_push + bi}))));
     }
     LQ_TRY(p2p_barrier(c));
@@ -1077,6 +1083,12 @@ static int gauss_field(lq_ctx* c) {
   }
 #endif
   ProfScope ps(c, LQ_PROF_GAUSS_FIELD);
+#if defined(LQ_HAVE_TUNED) && !defined(LQ_HOST_EMU)
+  if (lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+    LQ_CHECK(lq_tuned_gauss_field(c->stream, c->g, c->U, c->E, c->G, nullptr));
+    c->launches++;
+  } else
+#endif
   LQ_DISPATCH(c, LQ_TRY((launch(c, c->g.vol, KGaussField<DD>{c->g, c->U, c->E, c->G, nullptr}))));
   c->halo_ok[2] = false;
   c->g_valid = true;
@@ -1113,6 +1125,12 @@ int lq_gauss_project_step(lq_ctx* c) {
   LQ_TRY(ensure_buf(&c->E2, c->e_bytes(), c));
   if (!(c->flags & LQ_FLAG_GAUSS_FUSED)) {
     ProfScope ps(c, LQ_PROF_GAUSS_STEP);
+#if defined(LQ_HAVE_TUNED) && !defined(LQ_HOST_EMU)
+    if (lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+      LQ_CHECK(lq_tuned_gauss_step(c->stream, c->g, c->U, c->G, c->E, c->E2));
+      c->launches++;
+    } else
+#endif
     LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KGaussProjectStep<DD>{c->g, c->U, c->G, c->E, c->E2}))));
     // low-ghost links of the split directions: recomputed, not exchanged.  (Folding them into the launch above was
     // measured slower on 4 GPUs, 49.1 vs 42.9 ms per trajectory: the combined functor costs the main path occupancy.)

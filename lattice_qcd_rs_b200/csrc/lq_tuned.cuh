@@ -565,6 +565,135 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Gauss projection step, D = 4 (project_to_gauss_step, field.rs:1301-1337): the arithmetic of KGaussProjectStep
+// (lq_gauss_project_link) with the lean 32-bit addressing of V4 -- one thread per link, a warp = 32 consecutive site slots
+// of one direction.  The generic functor spends as many instructions on its 64-bit site decode as on the three products.
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_gstep4_kernel(LqGeom g, const cx* __restrict__ U, const cx* __restrict__ G, const cx* __restrict__ Ein,
+                     cx* __restrict__ Eout) {
+  constexpr int SITES = BLOCK / 4;
+  const int mu = threadIdx.x / SITES;
+  const int n = blockIdx.x * SITES + (threadIdx.x - mu * SITES);
+  if (n >= (int)g.vol) return;
+  const int e0 = g.ext[0], ne0 = g.ne0;
+  int row = n / e0;
+  const int lane = n - row * e0;
+  const int x0 = lane < ne0 ? 2 * lane : 2 * (lane - ne0) + 1;
+  int q = row / g.ext[1];
+  const int x1 = row - q * g.ext[1] + g.ghost[1];
+  row = q;
+  q = row / g.ext[2];
+  const int x2 = row - q * g.ext[2] + g.ghost[2];
+  const int x3 = q + g.ghost[3];
+  const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
+  const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
+  const int p = x1 * s1 + x2 * s2 + x3 * s3 + sl0;
+  int up;
+  if (mu == 0) {
+    const int x0p = x0 + 1 < e0 ? x0 + 1 : 0;
+    up = (x0p & 1) * ne0 + (x0p >> 1) - sl0;
+  } else if (mu == 1) {
+    up = x1 + 1 < g.sext[1] ? s1 : -x1 * s1;
+  } else if (mu == 2) {
+    up = x2 + 1 < g.sext[2] ? s2 : -x2 * s2;
+  } else {
+    up = x3 + 1 < g.sext[3] ? s3 : -x3 * s3;
+  }
+  const cx* gb = G + ((p >> 5) * 9) * 32 + (p & 31);
+  const int pp = p + up;
+  const cx* gpb = G + ((pp >> 5) * 9) * 32 + (pp & 31);
+  const int ee = ((p >> 5) * 16 + mu * 4) * 32 + (p & 31);
+  A8 e;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const cx v = __ldcs(Ein + ee + k * 32);
+    e.e[2 * k] = v.x;
+    e.e[2 * k + 1] = v.y;
+  }
+  const M3 u = lq_ld36(U, p, mu);
+  M3 gx, gp;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    gx.e[k] = __ldg(gb + k * 32);
+    gp.e[k] = __ldg(gpb + k * 32);
+  }
+  e = lq_gauss_project_link(u, gx, gp, e);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) __stcs(Eout + ee + k * 32, cmk(e.e[2 * k], e.e[2 * k + 1]));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Gauss field, D = 4 (EField::gauss, field.rs:1174-1195): the arithmetic and summation order of lq_gauss_site with the
+// lean 32-bit addressing; one thread per site.  PUSH: boundary sites also go straight into the neighbour ranks' ghost
+// layers (peer memory), as in KGaussField.
+template <int BLOCK, int MINB, int PUSH>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_gfield4_kernel(LqGeom g, const cx* __restrict__ U, const cx* __restrict__ E, cx* __restrict__ G,
+                      const LqPush* __restrict__ ps) {
+  const int n = blockIdx.x * BLOCK + threadIdx.x;
+  if (n >= (int)g.vol) return;
+  const int e0 = g.ext[0], ne0 = g.ne0;
+  int row = n / e0;
+  const int lane = n - row * e0;
+  const int x0 = lane < ne0 ? 2 * lane : 2 * (lane - ne0) + 1;
+  int q = row / g.ext[1];
+  const int x1 = row - q * g.ext[1] + g.ghost[1];
+  row = q;
+  q = row / g.ext[2];
+  const int x2 = row - q * g.ext[2] + g.ghost[2];
+  const int x3 = q + g.ghost[3];
+  const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
+  const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
+  const int p = x1 * s1 + x2 * s2 + x3 * s3 + sl0;
+  const int x0m = x0 > 0 ? x0 - 1 : e0 - 1;
+  const int dn[4] = {(x0m & 1) * ne0 + (x0m >> 1) - sl0, x1 > 0 ? -s1 : (g.sext[1] - 1) * s1,
+                     x2 > 0 ? -s2 : (g.sext[2] - 1) * s2, x3 > 0 ? -s3 : (g.sext[3] - 1) * s3};
+  M3 acc = m3_zero();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pm = p + dn[i];
+    A8 eo, em;
+    const cx* eb = E + ((p >> 5) * 16 + i * 4) * 32 + (p & 31);
+    const cx* mb = E + ((pm >> 5) * 16 + i * 4) * 32 + (pm & 31);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const cx a = __ldg(eb + k * 32), b = __ldg(mb + k * 32);
+      eo.e[2 * k] = a.x;
+      eo.e[2 * k + 1] = a.y;
+      em.e[2 * k] = b.x;
+      em.e[2 * k + 1] = b.y;
+    }
+    acc = m3_add(acc, lq_adjoint_to_matrix(eo));
+    const M3 u = lq_ld36(U, pm, i);
+    const M3 t = m3_mul_dn(u, lq_adjoint_to_matrix(em));  // U^+ E
+    M3 neg = m3_zero();
+    m3_fma_nn(neg, t, u);
+    acc = m3_sub(acc, neg);
+  }
+  cx* gb = G + ((p >> 5) * 9) * 32 + (p & 31);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) gb[k * 32] = acc.e[k];
+  if (PUSH) {
+    const int o2 = g.ghost[2] ? (x2 == 1 ? 0 : (x2 == g.ext[2] ? 2 : 1)) : 1;
+    const int o3 = g.ghost[3] ? (x3 == 1 ? 0 : (x3 == g.ext[3] ? 2 : 1)) : 1;
+    if (o2 != 1 || o3 != 1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {  // z-face, t-face, zt-corner neighbour
+        const int a = c == 1 ? 1 : o2, bb = c == 0 ? 1 : o3;
+        if ((a == 1 && bb == 1) || (c == 2 && (o2 == 1 || o3 == 1))) continue;
+        const int nb = ps->nbmap[a][bb];
+        if (nb < 0) continue;
+        const int pd = p + ps->delta[nb];
+        cx* d = ps->peer[nb] + ((pd >> 5) * 9) * 32 + (pd & 31);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) d[k * 32] = acc.e[k];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Metropolis sub-step (one direction, one colour), D = 4: MetropolisHastingsSweep (metropolis_hastings_sweep.rs:126-174)
 // with the lean addressing of lq_sweep4_kernel and the same arithmetic as KMetropolis (staple order nu ascending, up
 // then down; proposal draws, then the accept draw, from the link's Philox stream).  The block's (#accepted, sum of
@@ -844,6 +973,20 @@ static inline cudaError_t lq_tuned_links_aos(cudaStream_t st, const LqGeom& g, c
     if (e != cudaSuccess) return e;
     lq_aos4_tma_kernel<0><<<rows, 128, smem, st>>>(g, U, aos);
   }
+  return cudaGetLastError();
+}
+static inline cudaError_t lq_tuned_gauss_field(cudaStream_t st, const LqGeom& g, const cx* U, const cx* E, cx* G,
+                                               const LqPush* d_ps) {
+  constexpr int BLOCK = 128;
+  const unsigned nb = (unsigned)((g.vol + BLOCK - 1) / BLOCK);
+  if (d_ps) lq_gfield4_kernel<BLOCK, 3, 1><<<nb, BLOCK, 0, st>>>(g, U, E, G, d_ps);
+  else lq_gfield4_kernel<BLOCK, 3, 0><<<nb, BLOCK, 0, st>>>(g, U, E, G, nullptr);
+  return cudaGetLastError();
+}
+static inline cudaError_t lq_tuned_gauss_step(cudaStream_t st, const LqGeom& g, const cx* U, const cx* G, const cx* Ein,
+                                              cx* Eout) {
+  constexpr int BLOCK = 128;
+  lq_gstep4_kernel<BLOCK, 4><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, G, Ein, Eout);
   return cudaGetLastError();
 }
 static inline lq_i64 lq_tuned_metropolis_blocks(const LqGeom& g) { return (g.vol / 2 + 127) / 128; }

@@ -405,6 +405,7 @@ def test_tuned_kernels_equal_generic_kernels(backend, ext):
     Uhb = o.sweep_heatbath(U, SEED_RNG, 31)
     Uor = o.sweep_overrelax(U, 1)
     Umh, nam, spm = o.sweep_metropolis(U, SEED_RNG, 41, n_update=2, spread=0.1, order=1, per_link=True)
+    Egs = o.project_to_gauss_step(U, E)
     res = []
     for flags in (0, FLAG_GENERIC_KERNELS):
         c = backend(4, ext, a=1.0, beta=6.0)
@@ -426,13 +427,20 @@ def test_tuned_kernels_equal_generic_kernels(backend, ext):
         c.sweep_overrelax(1)
         orx = c.links_download()
         assert rel(orx, Uor) <= 1e-9
+        # Gauss projection step (tuned: lq_gstep4_kernel)
+        c.links_upload(U)
+        c.efield_upload(E)
+        c.gauss_project_step()
+        gs = c.efield_download()
+        assert rel(gs, Egs) <= RTOL
         c.links_upload(U)
         na, sp = c.sweep_metropolis(SEED_RNG, 41, spread=0.1, n_update=2)
         assert na == nam and abs(sp - spm) <= 1e-9 * spm and rel(c.links_download(), Umh) <= 1e-9
-        res.append((md, hb, orx, pq, hl))
+        res.append((md, hb, orx, pq, hl, gs))
     assert rel(res[0][0][0], res[1][0][0]) <= 1e-14 and rel(res[0][0][1], res[1][0][1]) <= 1e-14
     assert rel(res[0][1], res[1][1]) <= 1e-12 and rel(res[0][2], res[1][2]) <= 1e-12
     assert abs(res[0][3] - res[1][3]) <= 1e-14 * abs(res[1][3]) and abs(res[0][4] - res[1][4]) <= 1e-13 * abs(res[1][4])
+    assert rel(res[0][5], res[1][5]) <= 1e-14
 
 
 @pytest.mark.parametrize("D,ext", [(4, [4, 4, 4, 4]), (3, [4, 6, 4])])

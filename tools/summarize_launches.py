@@ -10,7 +10,7 @@ import sys
 NL = 4 * 32 ** 4
 NS = 32 ** 4
 ALG = {  # kernel-name fragment -> algorithmic bytes per launch at 32^4
-    "lq_md4_kernel<128, 3, 1": 416 * NL, "lq_md4_kernel<128, 3, 0": 272 * NL, "KGaussField": 976 * NS,
+    "lq_md4_kernel<128, 3, 1": 416 * NL, "lq_md4_kernel<128, 3, 0": 272 * NL, "KGaussField": 976 * NS, "lq_gfield4_kernel": 976 * NS, "lq_gstep4_kernel": 308 * NL, "lq_metro4_kernel": 144 * NL + 144 * NL // 8,
     "KGaussProjectStep": 308 * NL, "KPlaquette": 144 * NL, "lq_plaq4_kernel": 144 * NL, "KEfieldEnergy": 64 * NL, "KReunitarize": 288 * NL,
     "KGaussDiv": 144 * NS, "KMomentaRefresh": 64 * NL, "lq_sweep4_kernel": 144 * NL + 144 * NL // 8,
     "KHeatBath": 144 * NL + 144 * NL // 8, "KOverrelax": 144 * NL + 144 * NL // 8, "KMetropolis": 144 * NL + 144 * NL // 8,
