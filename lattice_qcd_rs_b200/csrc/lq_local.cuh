@@ -439,7 +439,7 @@ LQ_HD void lq_svd3(const M3& a, M3& u, M3& v) {
         // the rotation's scalars from reciprocals (one division-class operation each instead of five divisions and
         // four square roots; the decomposition converges to the same factors, the iterates differ in the last bits)
         const double g2 = cnorm2(apq), pq = app * aqq;
-        if (g2 <= 1e-300 * 1e-300 || g2 <= 1e-34 * pq) continue;
+        if (g2 <= 0.0 || g2 <= 1e-34 * pq) continue;  // |apq| <= 1e-300 (underflows to 0 when squared) or <= 1e-17 sqrt(app aqq)
         const double rg = LQ_RSQRT(g2), gg = g2 * rg;  // gg = |apq|
         off = fmax(off, gg * LQ_RSQRT(pq));
         cx ph = cmk(apq.x * rg, apq.y * rg);
