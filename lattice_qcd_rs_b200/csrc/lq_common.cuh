@@ -94,9 +94,27 @@ LQ_HD lq_i64 lq_addr(lq_i64 p, int npl, int plane) { return ((p >> 5) * npl + pl
 
 // n in [0, vol) -> site.  Rows of x0 are walked "even x0 first, then odd x0" so that consecutive n (lanes of
 // a warp) touch consecutive memory in both halves of the plane.
+// (Ordinals below 2^31 -- every lattice that fits a GPU today -- take 32-bit divisions: a 64-bit division costs the
+// GPU some eighty instructions, and a thread of the streaming kernels has only a few hundred of useful work.)
 template <int D>
 LQ_HD Site<D> lq_site(const LqGeom& g, lq_i64 n) {
   Site<D> st;
+  if (n < ((lq_i64)1 << 31)) {
+    unsigned row = (unsigned)n / (unsigned)g.ext[0];
+    int lane = (int)((unsigned)n - row * (unsigned)g.ext[0]);
+    int x0 = lane < g.ne0 ? 2 * lane : 2 * (lane - g.ne0) + 1;
+    st.x[0] = x0 + g.ghost[0];
+    st.s = st.x[0];
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      unsigned q = row / (unsigned)g.ext[d];
+      int xd = (int)(row - q * (unsigned)g.ext[d]);
+      row = q;
+      st.x[d] = xd + g.ghost[d];
+      st.s += (lq_i64)st.x[d] * g.sstride[d];
+    }
+    return st;
+  }
   lq_i64 row = n / g.ext[0];
   int lane = (int)(n - row * g.ext[0]);
   int x0 = lane < g.ne0 ? 2 * lane : 2 * (lane - g.ne0) + 1;
@@ -143,10 +161,27 @@ template <int D>
 LQ_HD Site<D> lq_site_eo(const LqGeom& g, lq_i64 n, int parity) {
   Site<D> st;
   int h0 = g.ext[0] >> 1;
-  lq_i64 row = n / h0;
-  int k = (int)(n - row * h0);
   int psum = parity;
   st.s = 0;
+  if (n < ((lq_i64)1 << 31)) {  // 32-bit divisions, see lq_site
+    unsigned row = (unsigned)n / (unsigned)h0;
+    int k = (int)((unsigned)n - row * (unsigned)h0);
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      unsigned q = row / (unsigned)g.ext[d];
+      int xd = (int)(row - q * (unsigned)g.ext[d]);
+      row = q;
+      psum += xd + g.goff[d];
+      st.x[d] = xd + g.ghost[d];
+      st.s += (lq_i64)st.x[d] * g.sstride[d];
+    }
+    int x0 = 2 * k + ((psum + g.goff[0]) & 1);
+    st.x[0] = x0 + g.ghost[0];
+    st.s += st.x[0];
+    return st;
+  }
+  lq_i64 row = n / h0;
+  int k = (int)(n - row * h0);
 #pragma unroll
   for (int d = 1; d < D; ++d) {
     lq_i64 q = row / g.ext[d];

@@ -10,6 +10,13 @@
 // i -> (site ordinal n, dir): groups of 32 sites x D dirs; lanes of a warp share `dir` and walk consecutive sites.
 template <int D>
 LQ_HD bool lq_decode_link(const LqGeom& g, lq_i64 i, lq_i64& n, int& dir) {
+  if (i < ((lq_i64)1 << 31)) {  // 32-bit arithmetic, see lq_site
+    const unsigned blk = (unsigned)i / (unsigned)(LQ_SITES_PER_GROUP * D);
+    const int r = (int)((unsigned)i - blk * (unsigned)(LQ_SITES_PER_GROUP * D));
+    dir = r / LQ_SITES_PER_GROUP;
+    n = (lq_i64)(blk * LQ_SITES_PER_GROUP + (unsigned)(r - dir * LQ_SITES_PER_GROUP));
+    return n < g.vol;
+  }
   lq_i64 blk = i / (LQ_SITES_PER_GROUP * D);
   int r = (int)(i - blk * (LQ_SITES_PER_GROUP * D));
   dir = r / LQ_SITES_PER_GROUP;
