@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 // ------------------------------------------------------------------------------------------------------------
 // Gauss projection step, D = 4 (project_to_gauss_step, field.rs:1301-1337): the arithmetic of KGaussProjectStep
 // (lq_gauss_project_link) with the lean 32-bit addressing of V4 -- one thread per link, a warp = 32 consecutive site slots
-// of one direction.  The generic functor spends as many instructions on its 64-bit site decode as on the three products.
+// of one direction, read-only loads of U and G, streaming accesses of E (0.206 vs 0.2175 ms for the generic functor,
+// 0.216 vs 0.237 ms inside a trajectory at 32^4).
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
     lq_gstep4_kernel(LqGeom g, const cx* __restrict__ U, const cx* __restrict__ G, const cx* __restrict__ Ein,
