@@ -21,6 +21,10 @@ device raises).
   MetropolisHastingsSweep                          metropolis_hastings_sweep MetropolisHastingsSweep
   HybridMethodVec                                  hybrid.rs:248-268         HybridMethodVec
   StateInitializationError / MultiIntegrationError error.rs:93-133           exceptions of the same names
+  serde derives (feature serde-serialize)          state.rs:654, 1047        to_json / to_bincode / from_* (serde_io.py)
+  -- not in the crate, same surfaces -------------------------------------------------------------
+  Omelyan steps, exponential link update           (integrator/mod.rs:93)    OmelyanCuda (a SymplecticIntegrator)
+  SU(2)-sub-group over-relaxation                  (overrelaxation.rs)       OverrelaxationSweepSu2
 
 Differences that the drop-in cannot hide: sweeps visit links in even/odd checkerboard order
 instead of the reference's sequential index order, and every stochastic draw comes from Philox4x32-10 streams keyed
