@@ -236,6 +236,12 @@ class LatticeStateDefault:
     def link_matrix_owned(self):
         return np.array(self.link_matrix())
 
+    def set_flags(self, flags):
+        """Behaviour switches of the device state (include/lqcd_b200.h LQ_FLAG_*): 0 restates the crate as coded;
+        FLAG_PAULI3_FIXED | FLAG_UNIFORM_DIRECTION give the textbook heat bath."""
+        self._ctx.set_flags(flags)
+        return self
+
     def clone(self):
         st = type(self)(self._ctx.clone(), self._lattice)
         return st
