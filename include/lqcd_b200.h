@@ -164,13 +164,24 @@ int lq_sweep_overrelax(lq_ctx*, int kind);                                      
 int lq_sweep_metropolis(lq_ctx*, uint64_t seed, uint64_t counter, double spread, int n_update, int64_t* n_accept,
                         double* sum_prob);                              /* metropolis_hastings_sweep.rs:126-174 */
 
+/* MetropolisHastingsDeltaDiagnostic::next_element (metropolis_hastings.rs:374-417: ONE uniformly random link per call,
+ * proposal orthonormalize(random_su3_close_to_unity(spread)) * U, accept w.p. min(1, exp(-dS))), batched: the n_hits
+ * hits of a call sit on links of one (direction, colour) class drawn from the call's stream and each draws its site
+ * from its own Philox stream (seed, counter, hit index), so they do not enter each other's staples; of two hits on the
+ * same link the lower index is performed and the other dropped (n_performed <= n_hits).  n_hits = 1 is the reference's
+ * call.  force_accept = 1 applies every proposal without the accept step (MetropolisHastings::potential_next_element,
+ * metropolis_hastings.rs:96-118).  Single-rank contexts with even extents. */
+int lq_metropolis_hits(lq_ctx*, uint64_t seed, uint64_t counter, double spread, int64_t n_hits, int force_accept,
+                       int64_t* n_performed, int64_t* n_accept, double* sum_prob);
+
 /* ---- HMC (hybrid_monte_carlo.rs:465-471, 573-613) ----------------------------------------------------------- */
-int lq_snapshot(lq_ctx*);                          /* keep (U,E,t) on the device for the reject path */
-int lq_restore(lq_ctx*);
+int lq_snapshot(lq_ctx*);                          /* keep a copy of (U, E, t) on the device ...                 */
+int lq_restore(lq_ctx*);                           /* ... and go back to it (LQ_E_NOSNAPSHOT if there is none)   */
 /* refresh (unless use_current_e) -> optional Gauss projection -> H_old -> n symplectic steps -> H_new ->
  * Bernoulli(clamp(exp(H_old-H_new),0,1)) from Philox stream (seed, counter, 0xFFFFFFFFFE); on reject the links
- * (and t) are restored.  On a decomposed context the energies returned are rank-local partial sums and NO accept
- * decision is taken (accept_mode = 0); the caller all-reduces and calls lq_restore itself. */
+ * (and t) are restored from the trajectory's own device copy (not the lq_snapshot buffers).  On a decomposed context
+ * with lq_set_comm registered the energies are global sums and every rank takes the same decision; without callbacks
+ * they are rank-local partial sums and the decision is rank-local -- do not use that configuration for production. */
 int lq_hmc_trajectory(lq_ctx*, double dt, int64_t n_steps, uint64_t seed, uint64_t counter, double sigma,
                       int use_current_e, int do_project, double* h_old, double* h_new, double* prob, int* accepted,
                       int64_t* gauss_steps);
@@ -226,11 +237,20 @@ enum {
   LQ_PROF_GAUSS_STEP = 5,
   LQ_PROF_HEATBATH = 6,
   LQ_PROF_OVERRELAX = 7,
-  LQ_PROF_METROPOLIS = 8
+  LQ_PROF_METROPOLIS = 8,
+  LQ_PROF_REUNITARIZE = 9,
+  LQ_PROF_MOMENTA = 10,
+  LQ_PROF_EFIELD_ENERGY = 11,
+  LQ_PROF_GAUSS_DIV = 12,
+  LQ_PROF_COPY = 13             /* device-to-device copies of the HMC reject path */
 };
 int lq_profile_enable(lq_ctx*, int on);
 int lq_profile_reset(lq_ctx*);
 int lq_profile_get(lq_ctx*, int kernel_class, int64_t* launches, double* total_ms);
+/* The two ceilings the rooflines are quoted against, measured on this device in the caller's own run: f64 FMA issue
+ * rate (TFLOP/s; eight independent chains per thread on every SM, ~20 ms) and a streaming copy of the link buffer
+ * (GB/s read + write).  Either pointer may be NULL. */
+int lq_measure_peaks(lq_ctx*, double* fp64_tflops, double* copy_gbs);
 
 #ifdef __cplusplus
 }

@@ -103,6 +103,7 @@ SYMBOLS = {
     "lq_sweep_heatbath": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_double]),
     "lq_sweep_overrelax": (C.c_int, [_vp, C.c_int]),
     "lq_sweep_metropolis": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_double, C.c_int, _i64p, _dp]),
+    "lq_metropolis_hits": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_double, C.c_int64, C.c_int, _i64p, _i64p, _dp]),
     "lq_snapshot": (C.c_int, [_vp]),
     "lq_restore": (C.c_int, [_vp]),
     "lq_hmc_trajectory": (C.c_int, [_vp, C.c_double, C.c_int64, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_int,
@@ -121,9 +122,11 @@ SYMBOLS = {
     "lq_profile_enable": (C.c_int, [_vp, C.c_int]),
     "lq_profile_reset": (C.c_int, [_vp]),
     "lq_profile_get": (C.c_int, [_vp, C.c_int, _i64p, _dp]),
+    "lq_measure_peaks": (C.c_int, [_vp, _dp, _dp]),
 }
 PROF = {"efield_link_step": 0, "efield_step": 1, "link_step": 2, "plaquette": 3, "gauss_field": 4, "gauss_step": 5,
-        "heatbath": 6, "overrelax": 7, "metropolis": 8}
+        "heatbath": 6, "overrelax": 7, "metropolis": 8, "reunitarize": 9, "momenta": 10, "efield_energy": 11,
+        "gauss_div": 12, "copy": 13}
 
 
 def bind(path):
@@ -189,6 +192,7 @@ class Context:
         self.ns = int(self.lib.lq_num_sites(self._h))
         self.nl = int(self.lib.lq_num_links(self._h))
         self._comm_keepalive = None
+        self._borrowed = False
 
     # -- plumbing
     def _check(self, rc, where):
@@ -205,11 +209,24 @@ class Context:
         new = object.__new__(Context)
         new.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_h"})
         new._h = h
+        new._borrowed = False
         return new
+
+    def borrowed(self, handle):
+        """A non-owning view of another lq_ctx* with this context's geometry (the handle a halo callback receives: this
+        context itself or a clone of it); closing the view does not destroy the context."""
+        if handle is None or handle == self._h.value:
+            return self
+        v = object.__new__(Context)
+        v.__dict__.update({k: x for k, x in self.__dict__.items() if k != "_h"})
+        v._h = _vp(handle)
+        v._borrowed = True
+        return v
 
     def close(self):
         if getattr(self, "_h", None):
-            self.lib.lq_ctx_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                self.lib.lq_ctx_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -252,11 +269,12 @@ class Context:
         return int(self.lib.lq_kernel_launches(self._h))
 
     def set_comm(self, halo_exchange, allreduce_sum, allreduce_sum_device=None):
-        """halo_exchange(which) -> int, allreduce_sum(numpy view of n doubles) -> int,
+        """halo_exchange(ctx_handle, which) -> int (the handle is the lq_ctx* the library asks the refresh for: this
+        context or a clone of it), allreduce_sum(numpy view of n doubles) -> int,
         allreduce_sum_device(pointer, n) -> int (optional: in-place sum in the library's result buffer)."""
         def _halo(user, ctx, which):
             try:
-                return int(halo_exchange(which) or 0)
+                return int(halo_exchange(ctx, which) or 0)
             except Exception:  # never unwind across the ABI
                 import traceback
                 traceback.print_exc()
@@ -437,6 +455,14 @@ class Context:
                     "lq_sweep_metropolis")
         return na.value, sp.value
 
+    def metropolis_hits(self, seed, counter, spread=0.1, n_hits=1, force_accept=False):
+        """n_hits random single-link Metropolis hits (MetropolisHastingsDeltaDiagnostic, one hit = the reference's call).
+        Returns (n_performed, n_accepted, sum of acceptance probabilities)."""
+        npf, na, sp = C.c_int64(0), C.c_int64(0), C.c_double(0)
+        self._check(self.lib.lq_metropolis_hits(self._h, seed, counter, spread, int(n_hits), int(force_accept),
+                                                C.byref(npf), C.byref(na), C.byref(sp)), "lq_metropolis_hits")
+        return npf.value, na.value, sp.value
+
     # -- HMC
     def snapshot(self):
         self._check(self.lib.lq_snapshot(self._h), "lq_snapshot")
@@ -464,6 +490,12 @@ class Context:
         n, ms = C.c_int64(0), C.c_double(0)
         self._check(self.lib.lq_profile_get(self._h, PROF[kernel], C.byref(n), C.byref(ms)), "lq_profile_get")
         return n.value, ms.value
+
+    def measure_peaks(self):
+        """(f64 FMA TFLOP/s, streaming-copy GB/s) measured on this context's device now."""
+        f, b = C.c_double(0), C.c_double(0)
+        self._check(self.lib.lq_measure_peaks(self._h, C.byref(f), C.byref(b)), "lq_measure_peaks")
+        return f.value, b.value
 
     # -- halos
     def is_decomposed(self, d):

@@ -23,7 +23,8 @@
 #define LQ_P2P_NBUF 7      /* U U2 E E2 G G2 flags */
 #define LQ_P2P_MAXNB 8     /* 3^2 - 1 neighbours of a 2-D process grid */
 #define LQ_P2P_HANDLE 64   /* sizeof(cudaIpcMemHandle_t) */
-#define LQ_PROF_CAP 8192
+#define LQ_PROF_CAP 8192     /* event pairs in flight; a full ring is drained into the per-class totals */
+#define LQ_PROF_NCLASS 16
 
 static thread_local char g_cuda_err[512] = "";
 
@@ -109,6 +110,7 @@ struct lq_ctx {
   int odd_mask;  // bit d: ext[d] is odd (sweeps then use the colour classes of lq_site_class); 0 when all are even
   cx *U, *U2, *E, *E2, *G, *G2;
   cx *snapU, *snapE;
+  cx* hmcU;  // reject-path copy of lq_hmc_trajectory (its own buffer: lq_snapshot / lq_restore keep theirs)
   int64_t snap_t;
   bool has_snap;
   double* d_aos;
@@ -141,6 +143,8 @@ struct lq_ctx {
   cudaEvent_t* prof_ev;       // 2 * LQ_PROF_CAP events
 #endif
   int prof_class[LQ_PROF_CAP];
+  double prof_ms[LQ_PROF_NCLASS];     // per-class totals of the pairs already drained
+  int64_t prof_cnt[LQ_PROF_NCLASS];
   size_t u_bytes() const { return (size_t)g.nchunk * 32 * 9 * g.D * sizeof(cx); }
   size_t e_bytes() const { return (size_t)g.nchunk * 32 * 4 * g.D * sizeof(cx); }
   size_t g_bytes() const { return (size_t)g.nchunk * 32 * 9 * sizeof(cx); }
@@ -165,13 +169,32 @@ struct DeviceGuard {
   } while (0)
 #endif
 
+// Folds the recorded event pairs into the per-class totals (synchronises the stream) and empties the ring.
+static void prof_drain(lq_ctx* c) {
+#ifndef LQ_HOST_EMU
+  if (!c->prof_ev || c->prof_n == 0) return;
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < c->prof_n; ++i) {
+    float ms = 0.f;
+    const int cls = c->prof_class[i];
+    if (cls >= 0 && cls < LQ_PROF_NCLASS && cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]) == cudaSuccess) {
+      c->prof_ms[cls] += ms;
+      c->prof_cnt[cls] += 1;
+    }
+  }
+  c->prof_n = 0;
+#else
+  (void)c;
+#endif
+}
 // Times the launches issued while it is alive (one CUDA-event pair on the context stream) when profiling is on.
 struct ProfScope {
   lq_ctx* c;
   int slot;
   ProfScope(lq_ctx* c_, int cls) : c(c_), slot(-1) {
 #ifndef LQ_HOST_EMU
-    if (c->prof_on && c->prof_ev && c->prof_n < LQ_PROF_CAP) {
+    if (c->prof_on && c->prof_ev) {
+      if (c->prof_n >= LQ_PROF_CAP) prof_drain(c);  // one stream synchronisation per LQ_PROF_CAP timed launches
       slot = c->prof_n++;
       c->prof_class[slot] = cls;
       cudaEventRecord(c->prof_ev[2 * slot], c->stream);
@@ -528,6 +551,7 @@ int lq_ctx_destroy(lq_ctx* c) {
 #endif
   rt_free(c->snapU);
   rt_free(c->snapE);
+  rt_free(c->hmcU);
   rt_free(c->d_aos);
   rt_free(c->d_partial);
   rt_free(c->d_result);
@@ -605,7 +629,8 @@ int lq_is_decomposed(const lq_ctx* c, int dir) { return (c && dir >= 0 && dir < 
 // ---------------------------------------------------------------------------------------------- marshalling
 static int links_from_device_aos(lq_ctx* c, const double* d_aos) {
 #if defined(LQ_HAVE_TUNED) && !defined(LQ_HOST_EMU)
-  if (lq_tuned_aos_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+  // the bulk-copy (TMA) row kernel needs a 16-byte aligned AoS pointer; anything else takes the per-thread functor
+  if (lq_tuned_aos_ok(c->g) && ((uintptr_t)d_aos & 15) == 0 && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
     LQ_CHECK(lq_tuned_links_aos(c->stream, c->g, c->U, const_cast<double*>(d_aos), false));
     c->launches++;
   } else
@@ -623,7 +648,7 @@ static int efield_from_device_aos(lq_ctx* c, const double* d_aos) {
 }
 static int links_to_device_aos(lq_ctx* c, double* d_aos) {
 #if defined(LQ_HAVE_TUNED) && !defined(LQ_HOST_EMU)
-  if (lq_tuned_aos_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
+  if (lq_tuned_aos_ok(c->g) && ((uintptr_t)d_aos & 15) == 0 && !(c->flags & LQ_FLAG_GENERIC_KERNELS)) {
     LQ_CHECK(lq_tuned_links_aos(c->stream, c->g, c->U, d_aos, true));
     c->launches++;
     return LQ_OK;
@@ -770,7 +795,10 @@ int lq_hamiltonian_links(lq_ctx* c, double* h) {
 int lq_hamiltonian_efield(lq_ctx* c, double* h) {
   if (!c || !h) return LQ_E_BADARG;
   LQ_GUARD(c);
-  LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol, KEfieldEnergy<DD>{c->g, c->E}))));
+  {
+    ProfScope ps(c, LQ_PROF_EFIELD_ENERGY);
+    LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol, KEfieldEnergy<DD>{c->g, c->E}))));
+  }
   double v = c->h_result[0];
   LQ_TRY(global_sum(c, &v, 1));
   *h = v * c->beta;
@@ -1026,6 +1054,7 @@ int lq_leapfrog_n(lq_ctx* c, double dt, int64_t n) {
 int lq_reunitarize(lq_ctx* c) {
   if (!c) return LQ_E_BADARG;
   LQ_GUARD(c);
+  ProfScope ps(c, LQ_PROF_REUNITARIZE);
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KReunitarize<DD>{c->g, c->U}))));
   c->halo_ok[0] = false;
   c->g_valid = false;
@@ -1036,6 +1065,7 @@ int lq_reunitarize(lq_ctx* c) {
 int lq_momenta_refresh(lq_ctx* c, uint64_t seed, uint64_t counter, double sigma) {
   if (!c) return LQ_E_BADARG;
   LQ_GUARD(c);
+  ProfScope ps(c, LQ_PROF_MOMENTA);
   LQ_DISPATCH(c, LQ_TRY((launch(c, lq_link_items(c->g), KMomentaRefresh<DD>{c->g, c->E, seed, counter, sigma}))));
   c->halo_ok[1] = false;
   c->g_valid = false;
@@ -1109,7 +1139,10 @@ int lq_gauss_sum_div(lq_ctx* c, double* out) {
   if (!c || !out) return LQ_E_BADARG;
   LQ_GUARD(c);
   LQ_TRY(gauss_field(c));
-  LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol, KGaussDiv<DD>{c->g, c->G}))));
+  {
+    ProfScope ps(c, LQ_PROF_GAUSS_DIV);
+    LQ_DISPATCH(c, LQ_TRY((reduce(c, c->g.vol, KGaussDiv<DD>{c->g, c->G}))));
+  }
   double v = c->h_result[0];
   LQ_TRY(global_sum(c, &v, 1));
   *out = v;
@@ -1293,6 +1326,49 @@ int lq_sweep_metropolis(lq_ctx* c, uint64_t seed, uint64_t counter, double sprea
   return LQ_OK;
 }
 
+// MetropolisHastingsDeltaDiagnostic::next_element (metropolis_hastings.rs:374-417), n_hits independent single-link hits
+// per call (KMetropolisHits).  force_accept = 1: apply every proposal (MetropolisHastings::potential_next_element,
+// metropolis_hastings.rs:96-118; the caller then accepts or rejects the whole state on the Hamiltonians).
+int lq_metropolis_hits(lq_ctx* c, uint64_t seed, uint64_t counter, double spread, int64_t n_hits, int force_accept,
+                       int64_t* n_performed, int64_t* n_accept, double* sum_prob) {
+  if (!c || n_hits < 1 || n_hits > 0x7fffffff || !(spread > 0.0 && spread < 1.0)) return LQ_E_BADARG;
+  if (c->decomposed) return LQ_E_BADARG;  // single-rank contexts only
+  LQ_GUARD(c);
+  double acc[3] = {0.0, 0.0, 0.0};
+  ProfScope ps(c, LQ_PROF_METROPOLIS);
+  if (c->odd_mask) {
+    // lattices with an odd extent have no two-colour classes: the hits run one after the other, each on a uniformly
+    // random link (the reference's own sequence of calls)
+    for (int64_t h = 0; h < n_hits; ++h) {
+      LQ_DISPATCH(c, LQ_TRY((reduce(c, 1, KMetropolisHits<DD>{c->g, c->U, nullptr, 1, 0, 0, c->flags, force_accept, c->beta,
+                                                              c->CA, spread, seed, counter, (lq_i64)h}))));
+      for (int k = 0; k < 3; ++k) acc[k] += c->h_result[k];
+    }
+  } else {
+    const lq_i64 half = c->g.vol / 2;
+    if (half > 0x7fffffff) return LQ_E_BADARG;
+    LqStream pick(seed, counter, 0xFFFFFFFFFDull);
+    int dir = (int)(pick.uniform01() * c->g.D);
+    if (dir >= c->g.D) dir = c->g.D - 1;
+    const int parity = pick.uniform01() < 0.5 ? 0 : 1;
+    LQ_TRY(ensure_aos(c, (size_t)half * sizeof(int)));
+    int* claim = (int*)c->d_aos;
+    LQ_TRY(launch(c, half, KFillInt{claim, 0x7fffffff}));
+    LQ_DISPATCH(c, LQ_TRY((launch(c, n_hits, KNoReduce<KMetropolisHits<DD>>{{c->g, c->U, claim, 0, dir, parity, c->flags,
+                                                                            force_accept, c->beta, c->CA, spread, seed,
+                                                                            counter, 0}}))));
+    LQ_DISPATCH(c, LQ_TRY((reduce(c, n_hits, KMetropolisHits<DD>{c->g, c->U, claim, 1, dir, parity, c->flags, force_accept,
+                                                                 c->beta, c->CA, spread, seed, counter, 0}))));
+    for (int k = 0; k < 3; ++k) acc[k] = c->h_result[k];
+  }
+  c->halo_ok[0] = false;
+  c->g_valid = false;
+  if (n_accept) *n_accept = (int64_t)(acc[0] + 0.5);
+  if (sum_prob) *sum_prob = acc[1];
+  if (n_performed) *n_performed = (int64_t)(acc[2] + 0.5);
+  return LQ_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- HMC
 int lq_snapshot(lq_ctx* c) {
   if (!c) return LQ_E_BADARG;
@@ -1327,8 +1403,11 @@ int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint
   if (do_project) LQ_TRY(lq_gauss_project(c, 0, &gs));                      // state.rs:1100
   if (gauss_steps) *gauss_steps = gs;
   // keep the old links for the reject path (hybrid_monte_carlo.rs:603-611)
-  if (!c->snapU) LQ_TRY(rt_malloc((void**)&c->snapU, c->u_bytes()));
-  LQ_TRY(rt_copy(c->snapU, c->U, c->u_bytes(), D2D, c->stream));
+  if (!c->hmcU) LQ_TRY(rt_malloc((void**)&c->hmcU, c->u_bytes()));
+  {
+    ProfScope ps(c, LQ_PROF_COPY);
+    LQ_TRY(rt_copy(c->hmcU, c->U, c->u_bytes(), D2D, c->stream));
+  }
   int64_t t0 = c->t;
   double h0, h1;
   LQ_TRY(lq_hamiltonian_total(c, &h0));
@@ -1338,7 +1417,7 @@ int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint
   LqStream acc(seed, counter, 0xFFFFFFFFFEull);
   bool ok = acc.bernoulli(p);
   if (!ok) {
-    LQ_TRY(rt_copy(c->U, c->snapU, c->u_bytes(), D2D, c->stream));
+    LQ_TRY(rt_copy(c->U, c->hmcU, c->u_bytes(), D2D, c->stream));
     c->halo_ok[0] = false;
     c->g_valid = false;
     c->t = t0;
@@ -1348,6 +1427,72 @@ int lq_hmc_trajectory(lq_ctx* c, double dt, int64_t n_steps, uint64_t seed, uint
   if (prob) *prob = p;
   if (accepted) *accepted = ok ? 1 : 0;
   return LQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- device peaks
+// The two ceilings the rooflines are quoted against, measured on THIS device in the caller's run: f64 FMA issue rate
+// (eight independent chains per thread, every SM full) and a streaming copy of the link buffer into the second one.
+#ifndef LQ_HOST_EMU
+}  // extern "C"
+__global__ void lq_dfma_peak_k(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, cc = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, cc); a1 = fma(a1, b, cc); a2 = fma(a2, b, cc); a3 = fma(a3, b, cc);
+    a4 = fma(a4, b, cc); a5 = fma(a5, b, cc); a6 = fma(a6, b, cc); a7 = fma(a7, b, cc);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 1.2345e-300) out[0] = a0;
+}
+__global__ void lq_copy_peak_k(const double2* __restrict__ a, double2* __restrict__ b, lq_i64 n) {
+  lq_i64 i = (lq_i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const lq_i64 stride = (lq_i64)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) b[i] = a[i];
+}
+extern "C" {
+#endif
+int lq_measure_peaks(lq_ctx* c, double* fp64_tflops, double* copy_gbs) {
+  if (!c) return LQ_E_BADARG;
+#ifdef LQ_HOST_EMU
+  (void)fp64_tflops;
+  (void)copy_gbs;
+  return LQ_E_NODEVICE;
+#else
+  LQ_GUARD(c);
+  int sms = 0;
+  LQ_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  cudaEvent_t e0, e1;
+  LQ_CHECK(cudaEventCreate(&e0));
+  LQ_CHECK(cudaEventCreate(&e1));
+  float ms = 0.f;
+  if (fp64_tflops) {
+    const int iters = 40000, blocks = sms * 8, threads = 256;
+    lq_dfma_peak_k<<<blocks, threads, 0, c->stream>>>(c->d_result, 1000);
+    LQ_CHECK(cudaEventRecord(e0, c->stream));
+    lq_dfma_peak_k<<<blocks, threads, 0, c->stream>>>(c->d_result, iters);
+    LQ_CHECK(cudaEventRecord(e1, c->stream));
+    LQ_CHECK(cudaEventSynchronize(e1));
+    LQ_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *fp64_tflops = 2.0 * 8 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    c->launches += 2;
+  }
+  if (copy_gbs) {
+    LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
+    const lq_i64 n = (lq_i64)(c->u_bytes() / sizeof(cx));
+    const int reps = 5;
+    lq_copy_peak_k<<<sms * 16, 256, 0, c->stream>>>(c->U, c->U2, n);
+    LQ_CHECK(cudaEventRecord(e0, c->stream));
+    for (int r = 0; r < reps; ++r) lq_copy_peak_k<<<sms * 16, 256, 0, c->stream>>>(c->U, c->U2, n);
+    LQ_CHECK(cudaEventRecord(e1, c->stream));
+    LQ_CHECK(cudaEventSynchronize(e1));
+    LQ_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *copy_gbs = (double)reps * 2.0 * (double)c->u_bytes() / (ms * 1e-3) / 1e9;
+    c->launches += reps + 1;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  LQ_CHECK(cudaGetLastError());
+  return LQ_OK;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- profiling
@@ -1362,12 +1507,15 @@ int lq_profile_enable(lq_ctx* c, int on) {
   }
 #endif
   c->prof_on = on != 0;
-  c->prof_n = 0;
-  return LQ_OK;
+  return lq_profile_reset(c);
 }
 int lq_profile_reset(lq_ctx* c) {
   if (!c) return LQ_E_BADARG;
   c->prof_n = 0;
+  for (int k = 0; k < LQ_PROF_NCLASS; ++k) {
+    c->prof_ms[k] = 0.0;
+    c->prof_cnt[k] = 0;
+  }
   return LQ_OK;
 }
 int lq_profile_get(lq_ctx* c, int kernel_class, int64_t* launches, double* total_ms) {
@@ -1375,16 +1523,10 @@ int lq_profile_get(lq_ctx* c, int kernel_class, int64_t* launches, double* total
   LQ_GUARD(c);
   *launches = 0;
   *total_ms = 0.0;
-#ifndef LQ_HOST_EMU
-  LQ_TRY(rt_sync(c->stream));
-  for (int i = 0; i < c->prof_n; ++i) {
-    if (c->prof_class[i] != kernel_class) continue;
-    float ms = 0.f;
-    LQ_CHECK(cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
-    *total_ms += ms;
-    *launches += 1;
-  }
-#endif
+  if (kernel_class < 0 || kernel_class >= LQ_PROF_NCLASS) return LQ_E_BADARG;
+  prof_drain(c);
+  *launches = c->prof_cnt[kernel_class];
+  *total_ms = c->prof_ms[kernel_class];
   return LQ_OK;
 }
 
@@ -1560,6 +1702,9 @@ int lq_p2p_attach(lq_ctx* c, int n_peers, const void* peer_handles, int n_neighb
   if (!c->decomposed || !c->p2p_flags || n_peers < 1 || n_peers > LQ_P2P_MAXNB || n_neighbors < 1 ||
       n_neighbors > LQ_P2P_MAXNB)
     return LQ_E_BADARG;
+  // one attach per context: a second one would reuse flag slots that still hold the epochs of the first (every barrier
+  // would pass at once) and leak the mappings already opened
+  if (c->p2p_on || c->p2p_npeers) return LQ_E_BADARG;
   LQ_GUARD(c);
   const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)peer_handles;
   for (int q = 0; q < n_peers; ++q)

@@ -340,11 +340,75 @@ LQ_HD M3 m3_cscale(const M3& a, cx s) {
   for (int k = 0; k < 9; ++k) r.e[k] = cmul(a.e[k], s);
   return r;
 }
-// acc += A*B.  -DLQ_MATMUL_KOUTER selects a k-outermost two-pass ordering of the same FMAs (every accumulator sees
-// the same sequence, so the bits are identical) that puts 18 independent chains between two dependent DFMAs; ptxas
-// schedules the plain source order at least as well (measured: 0.655 vs 0.672 ms for the fused MD kernel), so it
-// stays an experiment switch.
-#ifndef LQ_MATMUL_KOUTER
+// acc += A*B and its two adjoint forms.  Every accumulator element sees the same sequence of FMAs as the plain
+// triple loop over (i, j, k) with cfma / cfma_c / cfma_ca innermost (k ascending; within one k the real and imaginary
+// updates in the order those helpers apply them), so the bits do not depend on the ordering chosen here.
+// Device ordering ("operand-stationary"): the FMAs are issued in runs of six that share one multiplicand -- a scalar
+// of A (nn, dn) or of B (nd) against the three columns / rows it meets.  A DFMA whose three register operands are all
+// fresh issues every ~2.9 cycles on sm_100 instead of every 2 (measured: 24.7 against 35.2 TFLOP/s); one operand held
+// over from the previous DFMA in the operand-reuse cache restores the full rate.  ptxas reorders plain C++ FMAs freely
+// (its own order reuses an operand in ~40 % of the DFMAs, 28 TFLOP/s); `asm volatile` pins the order written here.
+#if defined(__CUDA_ARCH__) && !defined(LQ_PLAIN_FMA_ORDER)
+__device__ __forceinline__ double lq_vfma(double a, double b, double c) {
+  double d;
+  asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c));
+  return d;
+}
+LQ_HD void m3_fma_nn(M3& acc, const M3& a, const M3& b) {  // acc_ij += a_ik b_kj
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double ax = a.e[3 * i + k].x, ay = a.e[3 * i + k].y;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        acc.e[3 * i + j].x = lq_vfma(ax, b.e[3 * k + j].x, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = lq_vfma(ax, b.e[3 * k + j].y, acc.e[3 * i + j].y);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        acc.e[3 * i + j].x = lq_vfma(-ay, b.e[3 * k + j].y, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = lq_vfma(ay, b.e[3 * k + j].x, acc.e[3 * i + j].y);
+      }
+    }
+}
+LQ_HD void m3_fma_nd(M3& acc, const M3& a, const M3& b) {  // acc_ij += a_ik conj(b_jk)
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double bx = b.e[3 * j + k].x, by = b.e[3 * j + k].y;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        acc.e[3 * i + j].x = lq_vfma(a.e[3 * i + k].x, bx, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = lq_vfma(a.e[3 * i + k].y, bx, acc.e[3 * i + j].y);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        acc.e[3 * i + j].x = lq_vfma(a.e[3 * i + k].y, by, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = lq_vfma(-a.e[3 * i + k].x, by, acc.e[3 * i + j].y);
+      }
+    }
+}
+LQ_HD void m3_fma_dn(M3& acc, const M3& a, const M3& b) {  // acc_ij += conj(a_ki) b_kj
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double ax = a.e[3 * k + i].x, ay = a.e[3 * k + i].y;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        acc.e[3 * i + j].x = lq_vfma(ax, b.e[3 * k + j].x, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = lq_vfma(ax, b.e[3 * k + j].y, acc.e[3 * i + j].y);
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        acc.e[3 * i + j].x = lq_vfma(ay, b.e[3 * k + j].y, acc.e[3 * i + j].x);
+        acc.e[3 * i + j].y = lq_vfma(-ay, b.e[3 * k + j].x, acc.e[3 * i + j].y);
+      }
+    }
+}
+#else
 LQ_HD void m3_fma_nn(M3& acc, const M3& a, const M3& b) {
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -369,85 +433,36 @@ LQ_HD void m3_fma_dn(M3& acc, const M3& a, const M3& b) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) cfma_ca(acc.e[3 * i + j], a.e[3 * k + i], b.e[3 * k + j]);
 }
-#else
-LQ_HD void m3_fma_nn(M3& acc, const M3& a, const M3& b) {
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const cx x = a.e[3 * i + k], y = b.e[3 * k + j];
-        acc.e[3 * i + j].x = fma(x.x, y.x, acc.e[3 * i + j].x);
-        acc.e[3 * i + j].y = fma(x.x, y.y, acc.e[3 * i + j].y);
-      }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const cx x = a.e[3 * i + k], y = b.e[3 * k + j];
-        acc.e[3 * i + j].x = fma(-x.y, y.y, acc.e[3 * i + j].x);
-        acc.e[3 * i + j].y = fma(x.y, y.x, acc.e[3 * i + j].y);
-      }
-  }
-}
-// acc += A*B^dagger
-LQ_HD void m3_fma_nd(M3& acc, const M3& a, const M3& b) {
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const cx x = a.e[3 * i + k], y = b.e[3 * j + k];
-        acc.e[3 * i + j].x = fma(x.x, y.x, acc.e[3 * i + j].x);
-        acc.e[3 * i + j].y = fma(x.y, y.x, acc.e[3 * i + j].y);
-      }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const cx x = a.e[3 * i + k], y = b.e[3 * j + k];
-        acc.e[3 * i + j].x = fma(x.y, y.y, acc.e[3 * i + j].x);
-        acc.e[3 * i + j].y = fma(-x.x, y.y, acc.e[3 * i + j].y);
-      }
-  }
-}
-// acc += A^dagger*B
-LQ_HD void m3_fma_dn(M3& acc, const M3& a, const M3& b) {
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const cx x = a.e[3 * k + i], y = b.e[3 * k + j];
-        acc.e[3 * i + j].x = fma(x.x, y.x, acc.e[3 * i + j].x);
-        acc.e[3 * i + j].y = fma(x.x, y.y, acc.e[3 * i + j].y);
-      }
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const cx x = a.e[3 * k + i], y = b.e[3 * k + j];
-        acc.e[3 * i + j].x = fma(x.y, y.y, acc.e[3 * i + j].x);
-        acc.e[3 * i + j].y = fma(-x.y, y.x, acc.e[3 * i + j].y);
-      }
-  }
-}
 #endif
+// r = A*B etc.: the accumulators start from a zero ptxas cannot see through, so the first FMA of every element is an
+// ordinary link of its chain and the operand-stationary order above survives scheduling (with the literal zero the
+// eighteen chain heads have no predecessor and ptxas hoists them out of their runs)
+#if !defined(LQ_HOST_EMU)
+static __constant__ double lq_czero = 0.0;  // read through the constant bank: not foldable at compile time
+#endif
+LQ_HD M3 m3_zero_opaque() {
+#if defined(__CUDA_ARCH__) && !defined(LQ_PLAIN_FMA_ORDER)
+  const double z = lq_czero;
+  M3 r;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.e[k] = cmk(z, z);
+  return r;
+#else
+  return m3_zero();
+#endif
+}
 LQ_HD M3 m3_mul_nn(const M3& a, const M3& b) {
-  M3 r = m3_zero();
+  M3 r = m3_zero_opaque();
   m3_fma_nn(r, a, b);
   return r;
 }
 LQ_HD M3 m3_mul_nd(const M3& a, const M3& b) {
-  M3 r = m3_zero();
+  M3 r = m3_zero_opaque();
   m3_fma_nd(r, a, b);
   return r;
 }
 LQ_HD M3 m3_mul_dn(const M3& a, const M3& b) {
-  M3 r = m3_zero();
+  M3 r = m3_zero_opaque();
   m3_fma_dn(r, a, b);
   return r;
 }

@@ -767,6 +767,93 @@ struct KMetropolis {  // MetropolisHastingsSweep, metropolis_hastings_sweep.rs:1
   }
 };
 
+// Random single-link Metropolis hits (MetropolisHastingsDeltaDiagnostic::next_element, metropolis_hastings.rs:374-417:
+// ONE uniformly random link per call; proposal orthonormalize(random_su3_close_to_unity(spread)) * U, accepted with
+// probability min(1, exp(-dS))), batched: the n_hits hits of one call all sit on links of one (direction, colour)
+// class drawn by the host, so no two of them enter each other's staples, and each hit draws its site of that colour
+// from its own Philox stream (seed, counter, hit index).  Two hits on the same link: the lower hit index keeps it
+// (phase 0 claims with an atomic minimum, phase 1 performs the claimed hits), the others are dropped and reported.
+// With n_hits = 1 this is the reference's call: a uniformly random link.
+#if defined(LQ_HOST_EMU)
+#define LQ_ATOMIC_MIN(ptr, val)                \
+  do {                                         \
+    _Pragma("omp critical(lq_claim)") {        \
+      if ((val) < *(ptr)) *(ptr) = (val);      \
+    }                                          \
+  } while (0)
+#elif defined(__CUDA_ARCH__)
+#define LQ_ATOMIC_MIN(ptr, val) atomicMin((ptr), (val))
+#else
+#define LQ_ATOMIC_MIN(ptr, val) ((void)0)
+#endif
+template <int D>
+struct KMetropolisHits {
+  static constexpr int K = 3;  // (#accepted, sum of acceptance probabilities, #performed)
+  LqGeom g;
+  cx* U;
+  int* claim;  // one entry per site of the colour (vol / 2), preset to INT_MAX
+  int phase, dir, parity, flags, force_accept;
+  double beta, CA, spread;
+  uint64_t seed, counter;
+  lq_i64 hit0;  // index of the first hit of this launch (sequential mode launches one hit at a time)
+  LQ_HD void operator()(lq_i64 i, double* v) const {
+    LqStream rng(seed, counter, (uint64_t)(hit0 + i));
+    Site<D> x;
+    int dir = this->dir;
+    if (claim == nullptr) {
+      // sequential mode (lattices with an odd extent have no two-colour classes): one hit per launch on a uniformly
+      // random link -- the reference's own sequence of calls
+      lq_i64 n = (lq_i64)(rng.uniform01() * (double)g.vol);
+      if (n >= g.vol) n = g.vol - 1;
+      dir = (int)(rng.uniform01() * D);
+      if (dir >= D) dir = D - 1;
+      x = lq_site<D>(g, n);
+    } else {
+      const lq_i64 half = g.vol >> 1;
+      lq_i64 n = (lq_i64)(rng.uniform01() * (double)half);
+      if (n >= half) n = half - 1;
+      if (phase == 0) {
+        LQ_ATOMIC_MIN(claim + n, (int)i);
+        return;
+      }
+      if (claim[n] != (int)i) return;
+      x = lq_site_eo<D>(g, n, parity);
+    }
+    v[2] += 1.0;
+    const lq_i64 p = lq_slot<D>(g, x);
+    const M3 old = lq_load_link_rw(U, g, dir, p);
+    const M3 prop = lq_metropolis_proposal(old, 1, spread, rng, flags);
+    if (force_accept) {  // MetropolisHastings::potential_next_element: the caller accepts on the Hamiltonians
+      v[0] += 1.0;
+      v[1] += 1.0;
+      lq_store_link(U, g, dir, p, prop);
+      return;
+    }
+    const M3 a = lq_staple_sum<D>(U, g, x, dir);
+    const double proba = fmax(fmin(exp(-lq_delta_s(a, prop, old, beta, CA)), 1.0), 0.0);
+    v[1] += proba;
+    if (rng.bernoulli(proba)) {
+      v[0] += 1.0;
+      lq_store_link(U, g, dir, p, prop);
+    }
+  }
+};
+template <class F>
+struct KNoReduce {  // runs a reduction functor for its side effects only
+  F f;
+  LQ_HD void operator()(lq_i64 i) const {
+    double v[F::K];
+#pragma unroll
+    for (int k = 0; k < F::K; ++k) v[k] = 0.0;
+    f(i, v);
+  }
+};
+struct KFillInt {
+  int* p;
+  int val;
+  LQ_HD void operator()(lq_i64 i) const { p[i] = val; }
+};
+
 // ---------------------------------------------------------------------------------------------- halos
 // Face slices of a decomposed direction `hd`: n in [0, face sites) enumerates storage sites with x[hd] fixed
 // (all other directions over their full STORAGE extent, so later directions carry earlier ghosts = corners).

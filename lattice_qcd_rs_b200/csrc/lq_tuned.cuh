@@ -2,167 +2,17 @@
 //
 // Same arithmetic as the generic functors KEfieldStep / KEfieldLinkStep of lq_kernels.cuh (the parity tests run
 // both); what changes is the mapping of threads to links, the register budget and the memory-level parallelism.
+// Variants that were measured and not adopted live in tools/lq_md_variants.cuh (kbench only).
 #pragma once
 #include "lq_kernels.cuh"
 
 #ifndef LQ_HOST_EMU
 
-// MAP: 0 = row walk (lq_site), 1 = tile walk (lq_site_tiled)
-template <int MAP>
-__device__ __forceinline__ Site<4> lq_tuned_site(const LqGeom& g, lq_i64 n) {
-  if (MAP == 1) return lq_site_tiled<4>(g, n);
-  return lq_site<4>(g, n);
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// V1: one thread per link, a warp = 32 consecutive sites of one direction, block = (BLOCK/32) warps covering
-// BLOCK/4/32 site groups x 4 directions.  FUSED = 1 also performs the link step into Unew.
-template <int BLOCK, int MINB, int MAP, int FUSED>
-__global__ void __launch_bounds__(BLOCK, MINB)
-    lq_md_link_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef,
-                      double dt_e, double dt_u, double c_u, int nkick) {
-  constexpr int SITES = BLOCK / 4;
-  const int mu = threadIdx.x / SITES;
-  const lq_i64 n = (lq_i64)blockIdx.x * SITES + (threadIdx.x - mu * SITES);
-  if (n >= g.vol) return;
-  const Site<4> st = lq_tuned_site<MAP>(g, n);
-  const lq_i64 p = lq_slot<4>(g, st);
-  M3 a = lq_staple_sum<4>(U, g, st, mu);
-  M3 u = lq_load_link(U, g, mu, p);
-  M3 w = m3_mul_nn(u, a);
-  cx tr[8];
-  lq_trace_gen(w, tr);
-  A8 e = lq_load_e(E, g, mu, p);
-  for (int kk = 0; kk < nkick; ++kk) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
-  }
-  lq_store_e(E, g, mu, p, e);
-  if (FUSED) lq_store_link(Unew, g, mu, p, lq_link_update<4>(u, e, dt_u, c_u, 0));
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// V2: one thread per (link, nu): the three staple pairs of a link are computed by three warps in parallel and
-// summed through shared memory in a fixed order (nu ascending, as the serial loop does), which triples the
-// number of independent load streams per link.  Block = 32 sites x 4 mu x 3 nu-slots = 384 threads.
-template <int MINB, int MAP, int FUSED>
-__global__ void __launch_bounds__(384, MINB)
-    lq_md_nusplit_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef,
-                         double dt_e, double dt_u, double c_u, int nkick) {
-  __shared__ cx sm[8][9][32];  // partial sums of slots 1 and 2, for the 4 directions
-  const int lane = threadIdx.x & 31;
-  const int w = threadIdx.x >> 5;  // 0..11
-  const int mu = w / 3, slot = w - 3 * mu;
-  const int nu = slot < mu ? slot : slot + 1;
-  const lq_i64 n = (lq_i64)blockIdx.x * 32 + lane;
-  const bool live = n < g.vol;
-  Site<4> st;
-  lq_i64 p = 0;
-  M3 acc = m3_zero();
-  if (live) {
-    st = lq_tuned_site<MAP>(g, n);
-    p = lq_slot<4>(g, st);
-    const Site<4> xpm = lq_up<4>(g, st, mu);
-    {
-      const Site<4> xpn = lq_up<4>(g, st, nu);
-      M3 a = lq_load_link(U, g, nu, lq_slot<4>(g, xpm));
-      M3 b = lq_load_link(U, g, mu, lq_slot<4>(g, xpn));
-      M3 t = m3_mul_nd(a, b);
-      M3 c = lq_load_link(U, g, nu, p);
-      m3_fma_nd(acc, t, c);
-    }
-    {
-      const Site<4> xmn = lq_dn<4>(g, st, nu);
-      const Site<4> xpmmn = lq_dn<4>(g, xpm, nu);
-      M3 a = lq_load_link(U, g, mu, lq_slot<4>(g, xmn));
-      M3 b = lq_load_link(U, g, nu, lq_slot<4>(g, xpmmn));
-      M3 t = m3_mul_nn(a, b);
-      M3 c = lq_load_link(U, g, nu, lq_slot<4>(g, xmn));
-      m3_fma_dn(acc, t, c);
-    }
-    if (slot > 0) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) sm[mu * 2 + slot - 1][k][lane] = acc.e[k];
-    }
-  }
-  __syncthreads();
-  if (!live || slot != 0) return;
-  // fixed summation order: (slot0 + slot1) + slot2  == the serial nu-ascending accumulation up to rounding of
-  // the partial sums; deterministic run to run.
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    cx s1 = sm[mu * 2][k][lane], s2 = sm[mu * 2 + 1][k][lane];
-    acc.e[k] = cadd(cadd(acc.e[k], s1), s2);
-  }
-  M3 u = lq_load_link(U, g, mu, p);
-  M3 wm = m3_mul_nn(u, acc);
-  cx tr[8];
-  lq_trace_gen(wm, tr);
-  A8 e = lq_load_e(E, g, mu, p);
-  for (int kk = 0; kk < nkick; ++kk) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
-  }
-  lq_store_e(E, g, mu, p, e);
-  if (FUSED) lq_store_link(Unew, g, mu, p, lq_link_update<4>(u, e, dt_u, c_u, 0));
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// V3: as V1 but the loop over nu is NOT unrolled (3 iterations, nu = mu+1, mu+2, mu+3 mod 4): a third of the code,
-// so the kernel body stays inside the 32 KB instruction cache.
-template <int BLOCK, int MINB, int MAP, int FUSED>
-__global__ void __launch_bounds__(BLOCK, MINB)
-    lq_md_link_loop_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef,
-                           double dt_e, double dt_u, double c_u, int nkick) {
-  constexpr int SITES = BLOCK / 4;
-  const int mu = threadIdx.x / SITES;
-  const lq_i64 n = (lq_i64)blockIdx.x * SITES + (threadIdx.x - mu * SITES);
-  if (n >= g.vol) return;
-  const Site<4> st = lq_tuned_site<MAP>(g, n);
-  const lq_i64 p = lq_slot<4>(g, st);
-  const Site<4> xpm = lq_up<4>(g, st, mu);
-  const lq_i64 ppm = lq_slot<4>(g, xpm);
-  M3 acc = m3_zero();
-#pragma unroll 1
-  for (int j = 1; j < 4; ++j) {
-    const int nu = (mu + j) & 3;
-    const Site<4> xpn = lq_up<4>(g, st, nu);
-    const Site<4> xmn = lq_dn<4>(g, st, nu);
-    const Site<4> xpmmn = lq_dn<4>(g, xpm, nu);
-    const lq_i64 pmn = lq_slot<4>(g, xmn);
-    {
-      M3 a = lq_load_link(U, g, nu, ppm);
-      M3 b = lq_load_link(U, g, mu, lq_slot<4>(g, xpn));
-      M3 t = m3_mul_nd(a, b);
-      M3 c = lq_load_link(U, g, nu, p);
-      m3_fma_nd(acc, t, c);
-    }
-    {
-      M3 a = lq_load_link(U, g, mu, pmn);
-      M3 b = lq_load_link(U, g, nu, lq_slot<4>(g, xpmmn));
-      M3 t = m3_mul_nn(a, b);
-      M3 c = lq_load_link(U, g, nu, pmn);
-      m3_fma_dn(acc, t, c);
-    }
-  }
-  M3 u = lq_load_link(U, g, mu, p);
-  M3 w = m3_mul_nn(u, acc);
-  cx tr[8];
-  lq_trace_gen(w, tr);
-  A8 e = lq_load_e(E, g, mu, p);
-  for (int kk = 0; kk < nkick; ++kk) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
-  }
-  lq_store_e(E, g, mu, p, e);
-  if (FUSED) lq_store_link(Unew, g, mu, p, lq_link_update<4>(u, e, dt_u, c_u, 0));
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// V4: lean index arithmetic.  One thread per link, a warp = 32 consecutive site slots (one chunk of the chunked-SoA
+// Lean index arithmetic.  One thread per link, a warp = 32 consecutive site slots (one chunk of the chunked-SoA
 // layout when ext0 is a multiple of 32) of one direction.  All neighbour slots are p + (sum of per-direction
 // deltas): the eight deltas are computed once per thread, every matrix is one 32-bit element index -> IMAD.WIDE ->
-// nine LDG.128 with immediate offsets.  The loop over nu is not unrolled (instruction-cache resident body).
+// nine LDG.128 with immediate offsets.
 __device__ __forceinline__ int lq_sel4(int d, int a0, int a1, int a2, int a3) {
   return d == 0 ? a0 : d == 1 ? a1 : d == 2 ? a2 : a3;
 }
@@ -174,24 +24,135 @@ __device__ __forceinline__ M3 lq_ld36(const cx* __restrict__ U, int slot, int di
   for (int k = 0; k < 9; ++k) r.e[k] = __ldg(b + k * 32);
   return r;
 }
-// L2 prefetch of one link matrix of the warp (9 planes x the 128-byte lines its slots touch): a hint, two instructions per
-// thread.  The lanes of every group of 8 consecutive slots share one line per plane; lane k asks for plane k & 7, all
-// lanes for plane 8, so every (plane, line) pair is requested once or more whatever the rotation of lanes inside a row.
-template <int L1 = 0>
-__device__ __forceinline__ void lq_pf36(const cx* __restrict__ U, int slot, int dir) {
-  const int e = ((slot >> 5) * 36 + dir * 9) * 32 + (slot & 31);
-  const cx* b = U + e;
-  if (L1) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(b + (threadIdx.x & 7) * 32));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(b + 8 * 32));
-  } else {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (threadIdx.x & 7) * 32));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(b + 8 * 32));
+// site decode of the per-link kernels (row walk, even x0 first) and the slot deltas of the eight neighbours
+struct LqSite4 {
+  int x0, x1, x2, x3;  // storage coordinates
+  int p;               // slot
+  int up[4], dn[4];    // slot deltas
+};
+// slot and neighbour deltas from the storage coordinates
+__device__ __forceinline__ void lq_site4_fill(const LqGeom& g, LqSite4& s) {
+  const int e0 = g.ext[0], ne0 = g.ne0;
+  const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
+  const int sl0 = (s.x0 & 1) * ne0 + (s.x0 >> 1);
+  s.p = s.x1 * s1 + s.x2 * s2 + s.x3 * s3 + sl0;
+  const int x0p = s.x0 + 1 < e0 ? s.x0 + 1 : 0, x0m = s.x0 > 0 ? s.x0 - 1 : e0 - 1;
+  s.up[0] = (x0p & 1) * ne0 + (x0p >> 1) - sl0;
+  s.dn[0] = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
+  s.up[1] = s.x1 + 1 < g.sext[1] ? s1 : -s.x1 * s1;
+  s.dn[1] = s.x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
+  s.up[2] = s.x2 + 1 < g.sext[2] ? s2 : -s.x2 * s2;
+  s.dn[2] = s.x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
+  s.up[3] = s.x3 + 1 < g.sext[3] ? s3 : -s.x3 * s3;
+  s.dn[3] = s.x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
+}
+__device__ __forceinline__ LqSite4 lq_site4(const LqGeom& g, int n) {
+  LqSite4 s;
+  const int e0 = g.ext[0], ne0 = g.ne0;
+  int row = n / e0;
+  const int lane = n - row * e0;
+  s.x0 = lane < ne0 ? 2 * lane : 2 * (lane - ne0) + 1;
+  int q = row / g.ext[1];
+  s.x1 = row - q * g.ext[1] + g.ghost[1];
+  row = q;
+  q = row / g.ext[2];
+  s.x2 = row - q * g.ext[2] + g.ghost[2];
+  s.x3 = q + g.ghost[3];
+  lq_site4_fill(g, s);
+  return s;
+}
+// n-th site of colour `parity` (global coordinate sum & 1; even extents); gi = global reference-order SITE index
+// (RNG stream ids are gi * 4 + mu: results do not depend on the decomposition)
+__device__ __forceinline__ LqSite4 lq_site4_eo(const LqGeom& g, int n, int parity, lq_i64& gi) {
+  LqSite4 s;
+  const int h0 = g.ext[0] >> 1;
+  int row = n / h0;
+  const int k = n - row * h0;
+  int q = row / g.ext[1];
+  const int i1 = row - q * g.ext[1];
+  row = q;
+  q = row / g.ext[2];
+  const int i2 = row - q * g.ext[2];
+  const int i3 = q;
+  s.x0 = 2 * k + ((parity + i1 + g.goff[1] + i2 + g.goff[2] + i3 + g.goff[3] + g.goff[0]) & 1);
+  s.x1 = i1 + g.ghost[1];
+  s.x2 = i2 + g.ghost[2];
+  s.x3 = i3 + g.ghost[3];
+  gi = (lq_i64)(s.x0 + g.goff[0]) * g.gstride[0] + (lq_i64)(i1 + g.goff[1]) * g.gstride[1] +
+       (lq_i64)(i2 + g.goff[2]) * g.gstride[2] + (lq_i64)(i3 + g.goff[3]) * g.gstride[3];
+  lq_site4_fill(g, s);
+  return s;
+}
+// Staple sum around link (x, mu) in the accumulation order of lq_staple_sum (nu ascending, up then down: same bits as
+// the generic functors), as the straight-line software pipeline of lq_md4_body: every operand is requested one
+// product ahead of its first use.  `u` returns the link itself, read through the coherent path (the sweeps update it
+// in place) while the last product runs.
+__device__ __forceinline__ void lq_staples4(const cx* __restrict__ U, const cx* own, const LqSite4& s, int mu, M3& acc,
+                                            M3& u) {
+  const int p = s.p;
+  const int pm = p + lq_sel4(mu, s.up[0], s.up[1], s.up[2], s.up[3]);
+  const int n1 = mu == 0 ? 1 : 0, n2 = mu <= 1 ? 2 : 1, n3 = mu <= 2 ? 3 : 2;
+  const int u1 = lq_sel4(n1, s.up[0], s.up[1], s.up[2], s.up[3]), d1 = lq_sel4(n1, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
+  const int u2 = lq_sel4(n2, s.up[0], s.up[1], s.up[2], s.up[3]), d2 = lq_sel4(n2, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
+  const int u3 = lq_sel4(n3, s.up[0], s.up[1], s.up[2], s.up[3]), d3 = lq_sel4(n3, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
+  acc = m3_zero();
+  M3 a = lq_ld36(U, pm, n1);
+  M3 b = lq_ld36(U, p + u1, mu);
+  M3 c, t;
+#define LQ_STAGE_UP(NU, DN)      \
+  c = lq_ld36(U, p, NU);         \
+  t = m3_mul_nd(a, b);           \
+  a = lq_ld36(U, p + DN, mu);    \
+  b = lq_ld36(U, pm + DN, NU);   \
+  m3_fma_nd(acc, t, c);
+#define LQ_STAGE_DN(NU, DN, NEXTA, NEXTB) \
+  c = lq_ld36(U, p + DN, NU);    \
+  t = m3_mul_nn(a, b);           \
+  a = NEXTA;                     \
+  b = NEXTB;                     \
+  m3_fma_dn(acc, t, c);
+  LQ_STAGE_UP(n1, d1)
+  LQ_STAGE_DN(n1, d1, lq_ld36(U, pm, n2), lq_ld36(U, p + u2, mu))
+  LQ_STAGE_UP(n2, d2)
+  LQ_STAGE_DN(n2, d2, lq_ld36(U, pm, n3), lq_ld36(U, p + u3, mu))
+  LQ_STAGE_UP(n3, d3)
+  c = lq_ld36(U, p + d3, n3);
+  t = m3_mul_nn(a, b);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) u.e[k] = own[k * 32];
+  m3_fma_dn(acc, t, c);
+#undef LQ_STAGE_UP
+#undef LQ_STAGE_DN
+}
+// new boundary link / Gauss-field element -> the ghost layers of the neighbour ranks (peer memory over NVLink)
+template <int NPL, int NV>
+__device__ __forceinline__ void lq_push4(const LqGeom& g, const LqPush* __restrict__ ps, int x2, int x3, int p, int plane0,
+                                         const cx* v) {
+  const int o2 = g.ghost[2] ? (x2 == 1 ? 0 : (x2 == g.ext[2] ? 2 : 1)) : 1;
+  const int o3 = g.ghost[3] ? (x3 == 1 ? 0 : (x3 == g.ext[3] ? 2 : 1)) : 1;
+  if (o2 == 1 && o3 == 1) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {  // z-face, t-face, zt-corner neighbour
+    const int a = c == 1 ? 1 : o2, bb = c == 0 ? 1 : o3;
+    if ((a == 1 && bb == 1) || (c == 2 && (o2 == 1 || o3 == 1))) continue;
+    const int k = ps->nbmap[a][bb];
+    if (k < 0) continue;
+    const int pd = p + ps->delta[k];
+    cx* d = ps->peer[k] + ((pd >> 5) * NPL + plane0) * 32 + (pd & 31);
+#pragma unroll
+    for (int kk = 0; kk < NV; ++kk) d[kk * 32] = v[kk];
   }
 }
-// FLAGS: 32 / 128 = L2 / L1 prefetch of the next (half) stage (both measured slower), 1 = visit nu so that direction 3 (first touched from DRAM by most blocks) comes last, 2 = streaming
-// (evict-first) accesses for E and U', 4 = FAKE neighbours (perfect-locality bound, kbench only: wrong results)
-template <int BLOCK, int FUSED, int FLAGS, int PUSH>
+// Fused force + E kick (+ link step into Unew when FUSED; USE_EXP: U <- exp(i dt E) U instead of the Euler rule).
+// The staple sum is a chain of twelve 3x3 products,  t = a b^+, acc += t c^+  (up)  and  t = a b, acc += t^+ c  (down)
+// for nu ascending (the order of lq_staple_sum: same bits as the generic functor), written as STRAIGHT-LINE code with
+// every operand requested one product ahead of its first use: ptxas then software-pipelines the whole chain (loads of
+// product k+1 interleaved with the DFMAs of product k) inside the 168-register budget, where the rolled nu loop of
+// round 1 exposed the full load latency at the top of each of its three iterations (0.654 -> 0.60 ms at 32^4;
+// tools/kbench2.cu: v7; the variants that lost -- 128 / 96 register builds, two staples ahead, products fenced into
+// basic blocks, three threads per link -- are in tools/lq_md_variants.cuh with their numbers in profiles/r02c).
+// E and U' use streaming (evict-first) accesses.  PUSH: boundary links also go into the neighbour ranks' ghost layers.
+template <int BLOCK, int FUSED, int USE_EXP, int PUSH>
 __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restrict__ U, cx* __restrict__ Unew,
                                             cx* __restrict__ E, double coef, double dt_e, double dt_u, double c_u,
                                             int nkick, const LqPush* __restrict__ ps, int blk) {
@@ -199,100 +160,46 @@ __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restric
   const int mu = threadIdx.x / SITES;
   const int n = blk * SITES + (threadIdx.x - mu * SITES);
   if (n >= (int)g.vol) return;
-  // site decode (row walk, even x0 first)
-  const int e0 = g.ext[0], ne0 = g.ne0;
-  int row = n / e0;
-  const int lane = n - row * e0;
-  const int x0 = lane < ne0 ? 2 * lane : 2 * (lane - ne0) + 1;
-  int q = row / g.ext[1];
-  const int x1 = row - q * g.ext[1] + g.ghost[1];
-  row = q;
-  q = row / g.ext[2];
-  const int x2 = row - q * g.ext[2] + g.ghost[2];
-  const int x3 = q + g.ghost[3];
-  const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
-  const int p = x1 * s1 + x2 * s2 + x3 * s3 + (x0 & 1) * ne0 + (x0 >> 1);
-  // slot deltas of the eight neighbours
-  const int x0p = x0 + 1 < e0 ? x0 + 1 : 0, x0m = x0 > 0 ? x0 - 1 : e0 - 1;
-  const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
-  const int up0 = (x0p & 1) * ne0 + (x0p >> 1) - sl0, dn0 = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
-  int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
-  int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
-  int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
-  if (FLAGS & 4) up1 = up2 = up3 = dn1 = dn2 = dn3 = 0;
-  if (FLAGS & 8) {
-    // L2 prefetch for the blocks one wave ahead: the link chunk that will be their cold (+x3) neighbour row and
-    // their own E chunk.  One 128-byte line per thread.
-    constexpr int PFD = 640;
-    const int nch = (int)g.nchunk;
-    int cu = (p >> 5) + (s3 >> 5) + PFD * (SITES / 32);
-    cu -= cu >= nch ? nch : 0;
-    cu -= cu >= nch ? nch : 0;
-    int ce = (p >> 5) + PFD * (SITES / 32);
-    ce -= ce >= nch ? nch : 0;
-    const char* pu = (const char*)(U + (lq_i64)cu * 36 * 32);
-    const char* pe = (const char*)(E + (lq_i64)ce * 16 * 32);
-    const int t = threadIdx.x;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + t * 128));
-    if (t < 144 - BLOCK) asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + (BLOCK + t) * 128));
-    if (t < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe + t * 128));
-  }
-  const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
-  // E early: its latency hides behind the staples
+  const LqSite4 s = lq_site4(g, n);
+  const int p = s.p;
+  const int pm = p + lq_sel4(mu, s.up[0], s.up[1], s.up[2], s.up[3]);
   const int ee = ((p >> 5) * 16 + mu * 4) * 32 + (p & 31);
-  cx ev[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) ev[k] = (FLAGS & 2) ? __ldcs(E + ee + k * 32) : E[ee + k * 32];
+  // nu ascending with the own direction skipped
+  const int n1 = mu == 0 ? 1 : 0, n2 = mu <= 1 ? 2 : 1, n3 = mu <= 2 ? 3 : 2;
+  const int u1 = lq_sel4(n1, s.up[0], s.up[1], s.up[2], s.up[3]), d1 = lq_sel4(n1, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
+  const int u2 = lq_sel4(n2, s.up[0], s.up[1], s.up[2], s.up[3]), d2 = lq_sel4(n2, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
+  const int u3 = lq_sel4(n3, s.up[0], s.up[1], s.up[2], s.up[3]), d3 = lq_sel4(n3, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
   M3 acc = m3_zero();
-  auto staple_pair = [&](int j) {
-    // default: nu = mu+1, mu+2, mu+3 (mod 4); FLAGS&1: nu ascending with the own direction skipped (3 last)
-    const int nu = (FLAGS & 1) ? (j - 1 + (j - 1 >= mu ? 1 : 0)) : ((mu + j) & 3);
-    const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
-    if ((FLAGS & 32) && j < 3) {  // operands of the next pair: DRAM -> L2 while this pair is computed
-      const int n2 = (FLAGS & 1) ? (j + (j >= mu ? 1 : 0)) : ((mu + j + 1) & 3);
-      const int up2_ = lq_sel4(n2, up0, up1, up2, up3), dn2_ = lq_sel4(n2, dn0, dn1, dn2, dn3);
-      lq_pf36(U, pm, n2);
-      lq_pf36(U, p + up2_, mu);
-      lq_pf36(U, p, n2);
-      lq_pf36(U, p + dn2_, mu);
-      lq_pf36(U, pm + dn2_, n2);
-      lq_pf36(U, p + dn2_, n2);
-    }
-    {  // up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)
-      M3 a = lq_ld36(U, pm, nu);
-      M3 b = lq_ld36(U, p + upn, mu);
-      if (FLAGS & 128) {  // L1 prefetch half a stage ahead: the three operands of the down staple
-        lq_pf36<1>(U, p + dnn, mu);
-        lq_pf36<1>(U, pm + dnn, nu);
-        lq_pf36<1>(U, p + dnn, nu);
-      }
-      M3 t = m3_mul_nd(a, b);
-      M3 c = lq_ld36(U, p, nu);
-      m3_fma_nd(acc, t, c);
-    }
-    {  // down:  (U_mu(x-nu) U_nu(x+mu-nu))^+ U_nu(x-nu)
-      if ((FLAGS & 128) && j < 3) {  // ... and of the next up staple
-        const int n2 = (FLAGS & 1) ? (j + (j >= mu ? 1 : 0)) : ((mu + j + 1) & 3);
-        lq_pf36<1>(U, pm, n2);
-        lq_pf36<1>(U, p + lq_sel4(n2, up0, up1, up2, up3), mu);
-        lq_pf36<1>(U, p, n2);
-      }
-      M3 a = lq_ld36(U, p + dnn, mu);
-      M3 b = lq_ld36(U, pm + dnn, nu);
-      M3 t = m3_mul_nn(a, b);
-      M3 c = lq_ld36(U, p + dnn, nu);
-      m3_fma_dn(acc, t, c);
-    }
-  };
-  if (FLAGS & 64) {  // fully unrolled: the scheduler may start the loads of the next pair under the current one
-    staple_pair(1);
-    staple_pair(2);
-    staple_pair(3);
-  } else {
-#pragma unroll 1
-    for (int j = 1; j < 4; ++j) staple_pair(j);
-  }
-  M3 u = lq_ld36(U, p, mu);
+  M3 a = lq_ld36(U, pm, n1);
+  M3 b = lq_ld36(U, p + u1, mu);
+  M3 c, t;
+#define LQ_STAGE_UP(NU, DN)      /* up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x); then the (a, b) of the down staple */ \
+  c = lq_ld36(U, p, NU);         \
+  t = m3_mul_nd(a, b);           \
+  a = lq_ld36(U, p + DN, mu);    \
+  b = lq_ld36(U, pm + DN, NU);   \
+  m3_fma_nd(acc, t, c);
+#define LQ_STAGE_DN(NU, DN, NEXTA, NEXTB) /* down:  (U_mu(x-nu) U_nu(x+mu-nu))^+ U_nu(x-nu) */ \
+  c = lq_ld36(U, p + DN, NU);    \
+  t = m3_mul_nn(a, b);           \
+  a = NEXTA;                     \
+  b = NEXTB;                     \
+  m3_fma_dn(acc, t, c);
+  LQ_STAGE_UP(n1, d1)
+  LQ_STAGE_DN(n1, d1, lq_ld36(U, pm, n2), lq_ld36(U, p + u2, mu))
+  LQ_STAGE_UP(n2, d2)
+  LQ_STAGE_DN(n2, d2, lq_ld36(U, pm, n3), lq_ld36(U, p + u3, mu))
+  LQ_STAGE_UP(n3, d3)
+  cx ev[4];
+  c = lq_ld36(U, p + d3, n3);
+  t = m3_mul_nn(a, b);
+  a = lq_ld36(U, p, mu);  // the link itself, for U * A
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ev[k] = __ldcs(E + ee + k * 32);
+  m3_fma_dn(acc, t, c);
+#undef LQ_STAGE_UP
+#undef LQ_STAGE_DN
+  const M3 u = a;
   M3 w = m3_mul_nn(u, acc);
   cx tr[8];
   lq_trace_gen(w, tr);
@@ -307,55 +214,22 @@ __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restric
     for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (FLAGS & 2) __stcs(E + ee + k * 32, cmk(e.e[2 * k], e.e[2 * k + 1]));
-    else E[ee + k * 32] = cmk(e.e[2 * k], e.e[2 * k + 1]);
-  }
+  for (int k = 0; k < 4; ++k) __stcs(E + ee + k * 32, cmk(e.e[2 * k], e.e[2 * k + 1]));
   if (FUSED) {
-    M3 un = lq_link_update<4>(u, e, dt_u, c_u, (FLAGS & 256) ? 1 : 0);  // 256: U <- exp(i dt E) U instead of Euler
-    cx* b = Unew + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
+    M3 un = lq_link_update<4>(u, e, dt_u, c_u, USE_EXP);
+    cx* bo = Unew + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      if (FLAGS & 2) __stcs(b + k * 32, un.e[k]);
-      else b[k * 32] = un.e[k];
-    }
-    if (PUSH) {
-      const int o2 = g.ghost[2] ? (x2 == 1 ? 0 : (x2 == g.ext[2] ? 2 : 1)) : 1;
-      const int o3 = g.ghost[3] ? (x3 == 1 ? 0 : (x3 == g.ext[3] ? 2 : 1)) : 1;
-      if (o2 != 1 || o3 != 1) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {  // z-face, t-face, zt-corner neighbour
-          const int a = c == 1 ? 1 : o2, bb = c == 0 ? 1 : o3;
-          if ((a == 1 && bb == 1) || (c == 2 && (o2 == 1 || o3 == 1))) continue;
-          const int k = ps->nbmap[a][bb];
-          if (k < 0) continue;
-          const int pd = p + ps->delta[k];
-          cx* d = ps->peer[k] + ((pd >> 5) * 36 + mu * 9) * 32 + (pd & 31);
-#pragma unroll
-          for (int kk = 0; kk < 9; ++kk) d[kk * 32] = un.e[kk];
-        }
-      }
-    }
+    for (int k = 0; k < 9; ++k) __stcs(bo + k * 32, un.e[k]);
+    if (PUSH) lq_push4<36, 9>(g, ps, s.x2, s.x3, p, mu * 9, un.e);
   }
 }
 
-// FLAGS & 16: persistent walk -- the grid is a few blocks per SM and every block walks a CONTIGUOUS range of rows,
-// so the +-x1 neighbour rows of a row were touched by the same SM a moment ago (L1 hits instead of L2 round trips).
-template <int BLOCK, int MINB, int FUSED, int FLAGS = 0, int PUSH = 0>
+template <int BLOCK, int MINB, int FUSED, int USE_EXP = 0, int PUSH = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
     lq_md4_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef, double dt_e,
                   double dt_u, double c_u, int nkick, const LqPush* __restrict__ ps, int bps) {
   // ps: device-resident peer table, read by the threads of boundary slices only; bps: blocks per t-slice (0: keep
   // the natural block order)
-  if (FLAGS & 16) {
-    constexpr int SITES = BLOCK / 4;
-    const int nblk = ((int)g.vol + SITES - 1) / SITES;
-    const int per = (nblk + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int b0 = blockIdx.x * per, b1 = min(b0 + per, nblk);
-#pragma unroll 1
-    for (int b = b0; b < b1; ++b) lq_md4_body<BLOCK, FUSED, FLAGS, 0>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, ps, b);
-    return;
-  }
   int blk = blockIdx.x;
   if (PUSH && bps) {
     // The blocks of the two boundary t-slices are interleaved 1 : (S-1) with interior blocks over the first part of
@@ -376,185 +250,27 @@ __global__ void __launch_bounds__(BLOCK, MINB)
       blk = (sl == 0 ? 0 : sl == 1 ? g.ext[3] - 1 : sl - 1) * bps + r;
     }
   }
-  lq_md4_body<BLOCK, FUSED, FLAGS, PUSH>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, ps, blk);
+  lq_md4_body<BLOCK, FUSED, USE_EXP, PUSH>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, ps, blk);
 }
-
-// ------------------------------------------------------------------------------------------------------------
-// V5: V4 with the loads software-pipelined by hand.  The staple sum is a stream of six (A, B, C) triples; the
-// loads of the next triple are issued before the two matrix products of the current one, so a warp hides its own
-// L2/DRAM latency behind ~430 DFMAs instead of relying on the two other warps of its scheduler (ncu of V4: 39 %
-// of the stall samples are long-scoreboard waits on the first DFMA that touches a freshly loaded matrix).
-// PIPE: 1 = prefetch A,B of the next half-stage; 2 = also fence the order with compiler barriers.
-#define LQ_CBAR() asm volatile("" ::: "memory")
-template <int BLOCK, int MINB, int FUSED, int PIPE = 1>
-__global__ void __launch_bounds__(BLOCK, MINB)
-    lq_md5_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef, double dt_e,
-                  double dt_u, double c_u, int nkick) {
-  constexpr int SITES = BLOCK / 4;
-  const int mu = threadIdx.x / SITES;
-  const int n = blockIdx.x * SITES + (threadIdx.x - mu * SITES);
-  if (n >= (int)g.vol) return;
-  const int e0 = g.ext[0], ne0 = g.ne0;
-  int row = n / e0;
-  const int lane = n - row * e0;
-  const int x0 = lane < ne0 ? 2 * lane : 2 * (lane - ne0) + 1;
-  int q = row / g.ext[1];
-  const int x1 = row - q * g.ext[1] + g.ghost[1];
-  row = q;
-  q = row / g.ext[2];
-  const int x2 = row - q * g.ext[2] + g.ghost[2];
-  const int x3 = q + g.ghost[3];
-  const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
-  const int p = x1 * s1 + x2 * s2 + x3 * s3 + (x0 & 1) * ne0 + (x0 >> 1);
-  const int x0p = x0 + 1 < e0 ? x0 + 1 : 0, x0m = x0 > 0 ? x0 - 1 : e0 - 1;
-  const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
-  const int up0 = (x0p & 1) * ne0 + (x0p >> 1) - sl0, dn0 = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
-  const int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
-  const int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
-  const int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
-  const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
-  const int ee = ((p >> 5) * 16 + mu * 4) * 32 + (p & 31);
-  M3 acc = m3_zero();
-  // prologue: A, B of the first up-staple
-  int nu = (mu + 1) & 3;
-  int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
-  M3 a = lq_ld36(U, pm, nu);
-  M3 b = lq_ld36(U, p + upn, mu);
-  cx ev[4];
-#pragma unroll 1
-  for (int j = 1; j < 4; ++j) {
-    M3 c = lq_ld36(U, p, nu);
-    M3 ad = lq_ld36(U, p + dnn, mu);
-    M3 bd = lq_ld36(U, pm + dnn, nu);
-    if (PIPE & 2) LQ_CBAR();
-    {  // up:  U_nu(x+mu) U_mu^+(x+nu) U_nu^+(x)
-      M3 t = m3_mul_nd(a, b);
-      m3_fma_nd(acc, t, c);
-    }
-    if (PIPE & 2) LQ_CBAR();
-    c = lq_ld36(U, p + dnn, nu);
-    if (j < 3) {
-      nu = (mu + j + 1) & 3;
-      upn = lq_sel4(nu, up0, up1, up2, up3);
-      dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
-      a = lq_ld36(U, pm, nu);
-      b = lq_ld36(U, p + upn, mu);
-    } else {
-      a = lq_ld36(U, p, mu);  // the link itself, for U * A
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ev[k] = __ldcs(E + ee + k * 32);
-    }
-    if (PIPE & 2) LQ_CBAR();
-    {  // down:  (U_mu(x-nu) U_nu(x+mu-nu))^+ U_nu(x-nu)
-      M3 t = m3_mul_nn(ad, bd);
-      m3_fma_dn(acc, t, c);
-    }
-  }
-  const M3 u = a;
-  M3 w = m3_mul_nn(u, acc);
-  cx tr[8];
-  lq_trace_gen(w, tr);
-  A8 e;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    e.e[2 * k] = ev[k].x;
-    e.e[2 * k + 1] = ev[k].y;
-  }
-  for (int kk = 0; kk < nkick; ++kk) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) __stcs(E + ee + k * 32, cmk(e.e[2 * k], e.e[2 * k + 1]));
-  if (FUSED) {
-    M3 un = lq_link_update<4>(u, e, dt_u, c_u, 0);
-    cx* bo = Unew + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) __stcs(bo + k * 32, un.e[k]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // Checkerboard sweep sub-step (one direction mu, one colour), D = 4, with the lean addressing of V4: the staple sum
 // of KHeatBath / KOverrelax (same accumulation order: nu ascending, up then down => the same bits as the generic
 // functors) followed by the single-link rule.  KIND: 0 heat bath (heat_bath.rs:73-123), 1 over-relaxation
 // (overrelaxation.rs:86-110, 158-184).  Links of the updated (mu, colour) set never enter each other's staples, so
 // neighbours are read through the non-coherent path while the own link is read and written in place.
-// PF: 0 none; 1 = L2 prefetch of the operands of the next nu pair; 2 = of all 19 matrices at thread start
-template <int BLOCK, int MINB, int KIND, int PF = 0>
+template <int BLOCK, int MINB, int KIND>
 __global__ void __launch_bounds__(BLOCK, MINB)
     lq_sweep4_kernel(LqGeom g, cx* __restrict__ U, int mu, int parity, int flags, int or_kind, double coupling,
                      unsigned long long seed, unsigned long long counter) {
   const int n = blockIdx.x * BLOCK + threadIdx.x;
   if (n >= (int)(g.vol >> 1)) return;
-  const int e0 = g.ext[0], ne0 = g.ne0, h0 = e0 >> 1;
-  int row = n / h0;
-  const int k = n - row * h0;
-  int q = row / g.ext[1];
-  const int i1 = row - q * g.ext[1];
-  row = q;
-  q = row / g.ext[2];
-  const int i2 = row - q * g.ext[2];
-  const int i3 = q;
-  const int x0 = 2 * k + ((parity + i1 + g.goff[1] + i2 + g.goff[2] + i3 + g.goff[3] + g.goff[0]) & 1);
-  const int x1 = i1 + g.ghost[1], x2 = i2 + g.ghost[2], x3 = i3 + g.ghost[3];
-  const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
-  const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
-  const int p = x1 * s1 + x2 * s2 + x3 * s3 + sl0;
-  const int x0p = x0 + 1 < e0 ? x0 + 1 : 0, x0m = x0 > 0 ? x0 - 1 : e0 - 1;
-  const int up0 = (x0p & 1) * ne0 + (x0p >> 1) - sl0, dn0 = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
-  const int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
-  const int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
-  const int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
-  const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
-  M3 acc = m3_zero();
-  auto pf_pair = [&](int j2) {
-    const int n2 = j2 + (j2 >= mu ? 1 : 0);
-    const int u2 = lq_sel4(n2, up0, up1, up2, up3), d2 = lq_sel4(n2, dn0, dn1, dn2, dn3);
-    lq_pf36(U, pm, n2);
-    lq_pf36(U, p + u2, mu);
-    lq_pf36(U, p, n2);
-    lq_pf36(U, p + d2, mu);
-    lq_pf36(U, pm + d2, n2);
-    lq_pf36(U, p + d2, n2);
-  };
-  if (PF == 2) {
-    pf_pair(1);
-    pf_pair(2);
-    lq_pf36(U, p, mu);
-  }
-#pragma unroll 1
-  for (int j = 0; j < 3; ++j) {
-    const int nu = j + (j >= mu ? 1 : 0);  // ascending, own direction skipped
-    const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
-    if (PF == 1) {
-      if (j < 2) pf_pair(j + 1);
-      else lq_pf36(U, p, mu);
-    }
-    {
-      M3 a = lq_ld36(U, pm, nu);
-      M3 b = lq_ld36(U, p + upn, mu);
-      M3 t = m3_mul_nd(a, b);
-      M3 c = lq_ld36(U, p, nu);
-      m3_fma_nd(acc, t, c);
-    }
-    {
-      M3 a = lq_ld36(U, p + dnn, mu);
-      M3 b = lq_ld36(U, pm + dnn, nu);
-      M3 t = m3_mul_nn(a, b);
-      M3 c = lq_ld36(U, p + dnn, nu);
-      m3_fma_dn(acc, t, c);
-    }
-  }
-  cx* own = U + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
-  M3 u;
-#pragma unroll
-  for (int kk = 0; kk < 9; ++kk) u.e[kk] = own[kk * 32];
+  lq_i64 gi;
+  const LqSite4 s = lq_site4_eo(g, n, parity, gi);
+  cx* own = U + ((s.p >> 5) * 36 + mu * 9) * 32 + (s.p & 31);
+  M3 acc, u;
+  lq_staples4(U, own, s, mu, acc, u);
   M3 r;
   if (KIND == 0) {
-    // global reference-order link index = RNG stream id (results do not depend on the decomposition)
-    const lq_i64 gi = (lq_i64)(x0 + g.goff[0]) * g.gstride[0] + (lq_i64)(i1 + g.goff[1]) * g.gstride[1] +
-                      (lq_i64)(i2 + g.goff[2]) * g.gstride[2] + (lq_i64)(i3 + g.goff[3]) * g.gstride[3];
     LqStream rng(seed, counter, (uint64_t)(gi * 4 + mu));
     r = lq_heat_bath_link(u, acc, coupling, rng, flags);
   } else {
@@ -675,23 +391,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   cx* gb = G + ((p >> 5) * 9) * 32 + (p & 31);
 #pragma unroll
   for (int k = 0; k < 9; ++k) gb[k * 32] = acc.e[k];
-  if (PUSH) {
-    const int o2 = g.ghost[2] ? (x2 == 1 ? 0 : (x2 == g.ext[2] ? 2 : 1)) : 1;
-    const int o3 = g.ghost[3] ? (x3 == 1 ? 0 : (x3 == g.ext[3] ? 2 : 1)) : 1;
-    if (o2 != 1 || o3 != 1) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {  // z-face, t-face, zt-corner neighbour
-        const int a = c == 1 ? 1 : o2, bb = c == 0 ? 1 : o3;
-        if ((a == 1 && bb == 1) || (c == 2 && (o2 == 1 || o3 == 1))) continue;
-        const int nb = ps->nbmap[a][bb];
-        if (nb < 0) continue;
-        const int pd = p + ps->delta[nb];
-        cx* d = ps->peer[nb] + ((pd >> 5) * 9) * 32 + (pd & 31);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) d[k * 32] = acc.e[k];
-      }
-    }
-  }
+  if (PUSH) lq_push4<9, 9>(g, ps, x2, x3, p, 0, acc.e);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -707,52 +407,11 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   const int n = blockIdx.x * BLOCK + threadIdx.x;
   double v0 = 0.0, v1 = 0.0;
   if (n < (int)(g.vol >> 1)) {
-    const int e0 = g.ext[0], ne0 = g.ne0, h0 = e0 >> 1;
-    int row = n / h0;
-    const int k = n - row * h0;
-    int q = row / g.ext[1];
-    const int i1 = row - q * g.ext[1];
-    row = q;
-    q = row / g.ext[2];
-    const int i2 = row - q * g.ext[2];
-    const int i3 = q;
-    const int x0 = 2 * k + ((parity + i1 + g.goff[1] + i2 + g.goff[2] + i3 + g.goff[3] + g.goff[0]) & 1);
-    const int x1 = i1 + g.ghost[1], x2 = i2 + g.ghost[2], x3 = i3 + g.ghost[3];
-    const int s1 = (int)g.sstride[1], s2 = (int)g.sstride[2], s3 = (int)g.sstride[3];
-    const int sl0 = (x0 & 1) * ne0 + (x0 >> 1);
-    const int p = x1 * s1 + x2 * s2 + x3 * s3 + sl0;
-    const int x0p = x0 + 1 < e0 ? x0 + 1 : 0, x0m = x0 > 0 ? x0 - 1 : e0 - 1;
-    const int up0 = (x0p & 1) * ne0 + (x0p >> 1) - sl0, dn0 = (x0m & 1) * ne0 + (x0m >> 1) - sl0;
-    const int up1 = x1 + 1 < g.sext[1] ? s1 : -x1 * s1, dn1 = x1 > 0 ? -s1 : (g.sext[1] - 1) * s1;
-    const int up2 = x2 + 1 < g.sext[2] ? s2 : -x2 * s2, dn2 = x2 > 0 ? -s2 : (g.sext[2] - 1) * s2;
-    const int up3 = x3 + 1 < g.sext[3] ? s3 : -x3 * s3, dn3 = x3 > 0 ? -s3 : (g.sext[3] - 1) * s3;
-    const int pm = p + lq_sel4(mu, up0, up1, up2, up3);
-    M3 acc = m3_zero();
-#pragma unroll 1
-    for (int j = 0; j < 3; ++j) {
-      const int nu = j + (j >= mu ? 1 : 0);  // ascending, own direction skipped
-      const int upn = lq_sel4(nu, up0, up1, up2, up3), dnn = lq_sel4(nu, dn0, dn1, dn2, dn3);
-      {
-        M3 a = lq_ld36(U, pm, nu);
-        M3 b = lq_ld36(U, p + upn, mu);
-        M3 t = m3_mul_nd(a, b);
-        M3 c = lq_ld36(U, p, nu);
-        m3_fma_nd(acc, t, c);
-      }
-      {
-        M3 a = lq_ld36(U, p + dnn, mu);
-        M3 b = lq_ld36(U, pm + dnn, nu);
-        M3 t = m3_mul_nn(a, b);
-        M3 c = lq_ld36(U, p + dnn, nu);
-        m3_fma_dn(acc, t, c);
-      }
-    }
-    cx* own = U + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
-    M3 old;
-#pragma unroll
-    for (int kk = 0; kk < 9; ++kk) old.e[kk] = own[kk * 32];
-    const lq_i64 gi = (lq_i64)(x0 + g.goff[0]) * g.gstride[0] + (lq_i64)(i1 + g.goff[1]) * g.gstride[1] +
-                      (lq_i64)(i2 + g.goff[2]) * g.gstride[2] + (lq_i64)(i3 + g.goff[3]) * g.gstride[3];
+    lq_i64 gi;
+    const LqSite4 s = lq_site4_eo(g, n, parity, gi);
+    cx* own = U + ((s.p >> 5) * 36 + mu * 9) * 32 + (s.p & 31);
+    M3 acc, old;
+    lq_staples4(U, own, s, mu, acc, old);
     LqStream rng(seed, counter, (uint64_t)(gi * 4 + mu));
     const M3 prop = lq_metropolis_proposal(old, n_update, spread, rng, flags);
     const double proba = fmax(fmin(exp(-lq_delta_s(acc, prop, old, beta, CA)), 1.0), 0.0);
@@ -926,6 +585,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+#ifndef LQ_TUNED_NO_LAUNCHERS  /* tools/ experiments include the kernels without instantiating the product set */
 // launchers used by lq_capi.cu (D = 4; 32-bit element indices: fields below 2^31 elements, else the generic path)
 static inline bool lq_tuned_ok(const LqGeom& g) {
   return g.D == 4 && g.nchunk * 32 * 36 < ((lq_i64)1 << 31) && g.vol < ((lq_i64)1 << 31);
@@ -933,7 +593,7 @@ static inline bool lq_tuned_ok(const LqGeom& g) {
 static inline cudaError_t lq_tuned_efield_step(cudaStream_t st, const LqGeom& g, const cx* U, cx* E, double coef, double dt,
                                                int nkick) {
   constexpr int BLOCK = 128;
-  lq_md4_kernel<BLOCK, 3, 0, 2><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, nullptr, E, coef, dt,
+  lq_md4_kernel<BLOCK, 3, 0><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, nullptr, E, coef, dt,
                                                                                                 0.0, 0.0, nkick, nullptr, 0);
   return cudaGetLastError();
 }
@@ -943,9 +603,9 @@ static inline cudaError_t lq_tuned_efield_link_step(cudaStream_t st, const LqGeo
   constexpr int BLOCK = 128;
   const unsigned nb = (unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4));
   if (use_exp)
-    lq_md4_kernel<BLOCK, 3, 1, 2 | 256><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0);
+    lq_md4_kernel<BLOCK, 3, 1, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0);
   else
-    lq_md4_kernel<BLOCK, 3, 1, 2><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0);
+    lq_md4_kernel<BLOCK, 3, 1, 0><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0);
   return cudaGetLastError();
 }
 static inline cudaError_t lq_tuned_sweep(cudaStream_t st, const LqGeom& g, cx* U, int kind /*0 hb, 1 or*/, int mu, int parity,
@@ -1016,10 +676,12 @@ static inline cudaError_t lq_tuned_efield_link_step_push(cudaStream_t st, const 
   const int bps = (g.ghost[3] && slice % (BLOCK / 4) == 0) ? (int)(slice / (BLOCK / 4)) : 0;
   const unsigned nb = (unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4));
   if (use_exp)
-    lq_md4_kernel<BLOCK, 3, 1, 2 | 256, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
+    lq_md4_kernel<BLOCK, 3, 1, 1, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
   else
-    lq_md4_kernel<BLOCK, 3, 1, 2, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
+    lq_md4_kernel<BLOCK, 3, 1, 0, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
   return cudaGetLastError();
 }
+
+#endif  // !LQ_TUNED_NO_LAUNCHERS
 
 #endif  // !LQ_HOST_EMU

@@ -130,8 +130,10 @@ class DistContext:
         return self._rank_of(c)
 
     # ------------------------------------------------------------------ callbacks
-    def _halo_exchange(self, which):
-        ctx = self.ctx
+    def _halo_exchange(self, handle, which):
+        # `handle` is the lq_ctx* the library wants refreshed: this rank's context or a clone of it (lq_ctx_clone copies
+        # the callbacks, not the peer-to-peer mappings, so a clone's ghost layers always travel through here)
+        ctx = self.ctx.borrowed(handle)
         for d in range(self.D):
             if not ctx.is_decomposed(d):
                 continue

@@ -19,7 +19,10 @@ device raises).
   HeatBathSweep                                    heat_bath.rs:40-157       HeatBathSweep
   OverrelaxationSweepRotation / Reverse            overrelaxation.rs         OverrelaxationSweepRotation / Reverse
   MetropolisHastingsSweep                          metropolis_hastings_sweep MetropolisHastingsSweep
-  HybridMethodVec                                  hybrid.rs:248-268         HybridMethodVec
+  HybridMethodVec / HybridMethodCouple(/Triple..)  hybrid.rs:248-268,330-446 HybridMethodVec, HybridMethodCouple, ...
+  MonteCarloDefault + McWrapper                    monte_carlo/mod.rs:117-293 MonteCarloDefault, McWrapper
+  MetropolisHastings(Diagnostic)                   metropolis_hastings.rs:40-  MetropolisHastings, ...Diagnostic
+  MetropolisHastingsDeltaDiagnostic                metropolis_hastings.rs:300- MetropolisHastingsDeltaDiagnostic
   StateInitializationError / MultiIntegrationError error.rs:93-133           exceptions of the same names
   serde derives (feature serde-serialize)          state.rs:654, 1047        to_json / to_bincode / from_* (serde_io.py)
   -- not in the crate, same surfaces -------------------------------------------------------------
@@ -622,13 +625,21 @@ class HybridMonteCarloDiagnostic(MonteCarlo):
     def next_element(self, state):
         if self._n == 0:
             raise MultiIntegrationError("ZeroIntegration")
+        if not isinstance(self._integrator, SymplecticEulerCuda):
+            # the trajectory runs on the device: only the device integrators can drive it (the reference runs whatever
+            # SymplecticIntegrator it is given; a host integrator here would silently be replaced by another one)
+            raise TypeError("HybridMonteCarlo on a device state needs a SymplecticEulerCuda or OmelyanCuda integrator, "
+                            f"not {type(self._integrator).__name__}")
+        if not isinstance(state, LatticeStateDefault):
+            raise TypeError(f"expected a LatticeStateDefault (device state), not {type(state).__name__}")
         seed, counter = _draw(self._rng)
         try:
             ctx = state._touch()
-            select = getattr(self._integrator, "_select", None)
-            if select is not None:
-                select(ctx)  # SymplecticEulerCuda: the reference's integrator; OmelyanCuda: the option
-            r = ctx.hmc_trajectory(self._dt, self._n, seed, counter, sigma=0.5 / state.beta())
+            self._integrator._select(ctx)  # SymplecticEulerCuda: the reference's integrator; OmelyanCuda: the option
+            try:
+                r = ctx.hmc_trajectory(self._dt, self._n, seed, counter, sigma=0.5 / state.beta())
+            finally:
+                SymplecticEulerCuda._select(self._integrator, ctx)  # leave the context on the reference's integrator
         except LqError as e:
             raise _wrap(e)
         self._prob_replace_last, self._has_replace_last = r["prob"], r["accepted"]
@@ -748,4 +759,212 @@ class HybridMethodVec(MonteCarlo):
     def next_element(self, state):
         for m in self._methods:
             state = m.next_element(state)
+        return state
+
+
+class HybridMethodCoupleError(RuntimeError):
+    """hybrid.rs:281-293: ErrorFirst(e) | ErrorSecond(e)."""
+
+    def __init__(self, which, error):
+        self.which, self.error = which, error
+        super().__init__(f"{which}({error!r})")
+
+
+class HybridMethodCouple(MonteCarlo):
+    """hybrid.rs:330-393: two methods, one after the other; errors are tagged with the method that raised them."""
+
+    def __init__(self, method_1, method_2):
+        self._m1, self._m2 = method_1, method_2
+
+    new = classmethod(lambda cls, method_1, method_2: cls(method_1, method_2))
+
+    def method_1(self):
+        return self._m1
+
+    def method_2(self):
+        return self._m2
+
+    def deconstruct(self):
+        return self._m1, self._m2
+
+    def next_element(self, state):
+        try:
+            state = state.monte_carlo_step(self._m1)
+        except Exception as e:  # noqa: BLE001 -- the reference maps every error of method 1
+            raise HybridMethodCoupleError("ErrorFirst", e)
+        try:
+            return state.monte_carlo_step(self._m2)
+        except Exception as e:  # noqa: BLE001
+            raise HybridMethodCoupleError("ErrorSecond", e)
+
+
+def HybridMethodTriple(method_1, method_2, method_3):
+    """hybrid.rs:396-404: Couple(Couple(1, 2), 3)."""
+    return HybridMethodCouple(HybridMethodCouple(method_1, method_2), method_3)
+
+
+def HybridMethodQuadruple(method_1, method_2, method_3, method_4):
+    """hybrid.rs:410-429."""
+    return HybridMethodCouple(HybridMethodTriple(method_1, method_2, method_3), method_4)
+
+
+def HybridMethodQuintuple(method_1, method_2, method_3, method_4, method_5):
+    """hybrid.rs:435-446."""
+    return HybridMethodCouple(HybridMethodQuadruple(method_1, method_2, method_3, method_4), method_5)
+
+
+class MonteCarloDefault:
+    """monte_carlo/mod.rs:117-170: a method that only PROPOSES a state; `next_element_default` accepts it with
+    probability `probability_of_replacement(old, new)` = clamp(exp(H_links(old) - H_links(new)), 0, 1) -- both energies
+    are device reductions -- drawing the Bernoulli from the host generator, as the reference does from its `rng`."""
+
+    def potential_next_element(self, state, rng):
+        raise NotImplementedError
+
+    @staticmethod
+    def probability_of_replacement(old_state, new_state):
+        d = old_state.hamiltonian_links() - new_state.hamiltonian_links()
+        return max(min(math.exp(d) if d < 700.0 else math.inf, 1.0), 0.0)
+
+    def next_element_default(self, state, rng):
+        potential_next = self.potential_next_element(state, rng)
+        proba = max(min(self.probability_of_replacement(state, potential_next), 1.0), 0.0)
+        if _bernoulli(rng, proba):
+            return potential_next
+        return state
+
+
+def _bernoulli(rng, p):
+    """rand::distributions::Bernoulli from one u64 of the host generator."""
+    return (rng.next_u64() >> 11) * (1.0 / 9007199254740992.0) < p
+
+
+class McWrapper(MonteCarlo):
+    """monte_carlo/mod.rs:210-293: makes a MonteCarlo out of a MonteCarloDefault and a generator."""
+
+    def __init__(self, mcd, rng):
+        self._mcd, self._rng = mcd, rng
+
+    new = classmethod(lambda cls, mcd, rng: cls(mcd, rng))
+
+    def mcd(self):
+        return self._mcd
+
+    def rng(self):
+        return self._rng
+
+    def rng_mut(self):
+        return self._rng
+
+    def deconstruct(self):
+        return self._mcd, self._rng
+
+    def next_element(self, state):
+        return self._mcd.next_element_default(state, self._rng)
+
+
+class MetropolisHastings(MonteCarloDefault):
+    """metropolis_hastings.rs:40-118: proposes a state in which `number_of_update` uniformly random links were multiplied
+    by orthonormalize(random_su3_close_to_unity(spread)); the whole state is then accepted or rejected on H_links
+    (MonteCarloDefault).  The proposal is a device clone + one batch of forced single-link hits (`lq_metropolis_hits`,
+    force_accept); hits that landed on a link already hit in the batch are dropped, so slightly fewer than
+    `number_of_update` links may change.  The reference calls this method "very slow" (:64-66): it recomputes the
+    Hamiltonian of the whole lattice per step; MetropolisHastingsSweep is the production path."""
+
+    def __init__(self, number_of_update, spread):
+        self._n, self._spread = int(number_of_update), float(spread)
+
+    @classmethod
+    def new(cls, number_of_update, spread):
+        """None for invalid parameters (metropolis_hastings.rs:73-85)."""
+        if number_of_update == 0 or spread <= 0.0 or spread >= 1.0:
+            return None
+        return cls(number_of_update, spread)
+
+    def number_of_update(self):
+        return self._n
+
+    def spread(self):
+        return self._spread
+
+    def potential_next_element(self, state, rng):
+        new = state.clone()
+        seed, counter = _draw(rng)
+        try:
+            new._touch().metropolis_hits(seed, counter, self._spread, self._n, force_accept=True)
+        except LqError as e:
+            raise _wrap(e)
+        return new
+
+
+class MetropolisHastingsDiagnostic(MetropolisHastings):
+    """metropolis_hastings.rs:160-290: the same with prob_replace_last / has_replace_last."""
+
+    def __init__(self, number_of_update, spread):
+        super().__init__(number_of_update, spread)
+        self._prob_replace_last, self._has_replace_last = 0.0, False
+
+    def prob_replace_last(self):
+        return self._prob_replace_last
+
+    def has_replace_last(self):
+        return self._has_replace_last
+
+    def next_element_default(self, state, rng):
+        potential_next = self.potential_next_element(state, rng)
+        proba = max(min(self.probability_of_replacement(state, potential_next), 1.0), 0.0)
+        self._prob_replace_last = proba
+        self._has_replace_last = _bernoulli(rng, proba)
+        return potential_next if self._has_replace_last else state
+
+
+class MetropolisHastingsDeltaDiagnostic(MonteCarlo):
+    """metropolis_hastings.rs:300-417 (the README's method): every call proposes a change of ONE uniformly random link
+    and accepts it on the local action difference delta_s_old_new_cmp (monte_carlo/mod.rs:324-334).
+
+    `hits_per_call` = 1 restates the reference call for call.  Larger values run that many independent hits per call in
+    one pair of launches (all on links of one random (direction, colour) class, so they do not see each other; hits
+    that collide on a link are dropped): the Markov chain is the same random-scan Metropolis, 10^4-10^5 times faster
+    per hit.  prob_replace_last() / has_replace_last() describe the last call: the mean acceptance probability of its
+    hits and whether any was accepted."""
+
+    def __init__(self, spread, rng, hits_per_call=1):
+        self._spread, self._rng, self._hits = float(spread), rng, int(hits_per_call)
+        self._prob_replace_last, self._has_replace_last = 0.0, False
+        self.hits_performed_last, self.hits_accepted_last = 0, 0
+
+    @classmethod
+    def new(cls, spread, rng, hits_per_call=1):
+        """None for an invalid spread (metropolis_hastings.rs:343-353)."""
+        if spread <= 0.0 or spread >= 1.0 or hits_per_call < 1:
+            return None
+        return cls(spread, rng, hits_per_call)
+
+    def prob_replace_last(self):
+        return self._prob_replace_last
+
+    def has_replace_last(self):
+        return self._has_replace_last
+
+    def spread(self):
+        return self._spread
+
+    def rng(self):
+        return self._rng
+
+    def rng_mut(self):
+        return self._rng
+
+    def rng_owned(self):
+        return self._rng
+
+    def next_element(self, state):
+        seed, counter = _draw(self._rng)
+        try:
+            n_perf, n_acc, sum_p = state._touch().metropolis_hits(seed, counter, self._spread, self._hits)
+        except LqError as e:
+            raise _wrap(e)
+        self.hits_performed_last, self.hits_accepted_last = n_perf, n_acc
+        self._prob_replace_last = sum_p / max(n_perf, 1)
+        self._has_replace_last = n_acc > 0
         return state

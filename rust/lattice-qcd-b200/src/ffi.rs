@@ -70,6 +70,11 @@ extern "C" {
     pub fn lq_sweep_overrelax(c: *mut lq_ctx, kind: c_int) -> c_int;
     pub fn lq_sweep_metropolis(c: *mut lq_ctx, seed: u64, counter: u64, spread: c_double, n_update: c_int,
                                n_accept: *mut i64, sum_prob: *mut c_double) -> c_int;
+    /// MetropolisHastingsDeltaDiagnostic::next_element (metropolis_hastings.rs:374-417), `n_hits` hits per call;
+    /// `force_accept` = 1: MetropolisHastings::potential_next_element (metropolis_hastings.rs:96-118)
+    pub fn lq_metropolis_hits(c: *mut lq_ctx, seed: u64, counter: u64, spread: c_double, n_hits: i64,
+                              force_accept: c_int, n_performed: *mut i64, n_accept: *mut i64,
+                              sum_prob: *mut c_double) -> c_int;
     /// HybridMonteCarloDiagnostic::next_element (hybrid_monte_carlo.rs:465-471, 573-613)
     pub fn lq_hmc_trajectory(c: *mut lq_ctx, dt: c_double, n_steps: i64, seed: u64, counter: u64, sigma: c_double,
                              use_current_e: c_int, do_project: c_int, h_old: *mut c_double, h_new: *mut c_double,

@@ -8,7 +8,12 @@
 //! (README.md:92-94 suggests it; E0117 rejects it).  So this crate defines its own synchronous state type that
 //! implements the reference's traits, re-uses the public generic `SimulationStateLeap<State, D>` (state.rs:856-861)
 //! for leap-frog states, and ships `MonteCarlo` impls with the constructor arguments and getters of the reference's
-//! `HybridMonteCarloDiagnostic` / `HeatBathSweep` / `OverrelaxationSweep*` / `MetropolisHastingsSweep`.
+//! `HybridMonteCarloDiagnostic` / `HeatBathSweep` / `OverrelaxationSweep*` / `MetropolisHastingsSweep` /
+//! `MetropolisHastingsDeltaDiagnostic`, plus a `MonteCarloDefault` impl (`MetropolisHastingsCuda`).  The reference's
+//! generic combinators need nothing from this crate: `McWrapper<MCD, State, Rng, D>` (monte_carlo/mod.rs:210-293),
+//! `HybridMethodVec` and `HybridMethodCouple/Triple/...` (hybrid.rs:248-446) are generic over any
+//! `State: LatticeState<D>` and any `MonteCarlo<State, D>` / `MonteCarloDefault<State, D>`, so they compose the types
+//! below as they are (the Python twin re-implements them only because it cannot import the crate).
 //!
 //! `LatticeState::link_matrix(&self) -> &LinkMatrix` hands out a HOST borrow (state.rs:74): the state keeps a lazily
 //! filled host mirror in a `OnceLock`; every mutation goes through `&mut self` or consumes `self`, where the mirror
@@ -528,5 +533,94 @@ impl<Rng: rand::Rng, const D: usize> MonteCarlo<LatticeStateCuda<D>, D> for Metr
         self.prob_replace_mean = sum_p / state.lattice.number_of_canonical_links_space() as f64;
         state.host_links = OnceLock::new();
         Ok(state)
+    }
+}
+
+/// metropolis_hastings.rs:300-417 (the README's method): one uniformly random link per call, accepted on the local
+/// action difference.  `hits_per_call` > 1 batches independent hits in one pair of launches (all on links of one random
+/// (direction, colour) class; hits colliding on a link are dropped); 1 restates the reference call for call.
+pub struct MetropolisHastingsDeltaDiagnosticCuda<Rng: rand::Rng> {
+    spread: Real,
+    hits_per_call: usize,
+    has_replace_last: bool,
+    prob_replace_last: Real,
+    rng: Rng,
+}
+impl<Rng: rand::Rng> MetropolisHastingsDeltaDiagnosticCuda<Rng> {
+    /// `None` for an invalid spread (metropolis_hastings.rs:343-353)
+    pub fn new(spread: Real, rng: Rng) -> Option<Self> {
+        Self::with_hits_per_call(spread, rng, 1)
+    }
+    pub fn with_hits_per_call(spread: Real, rng: Rng, hits_per_call: usize) -> Option<Self> {
+        if spread <= 0_f64 || spread >= 1_f64 || hits_per_call == 0 {
+            return None;
+        }
+        Some(Self { spread, hits_per_call, has_replace_last: false, prob_replace_last: 0.0, rng })
+    }
+    pub const fn prob_replace_last(&self) -> Real {
+        self.prob_replace_last
+    }
+    pub const fn has_replace_last(&self) -> bool {
+        self.has_replace_last
+    }
+    pub const fn spread(&self) -> Real {
+        self.spread
+    }
+    pub const fn rng(&self) -> &Rng {
+        &self.rng
+    }
+    pub fn rng_mut(&mut self) -> &mut Rng {
+        &mut self.rng
+    }
+    pub fn rng_owned(self) -> Rng {
+        self.rng
+    }
+}
+impl<Rng: rand::Rng, const D: usize> MonteCarlo<LatticeStateCuda<D>, D> for MetropolisHastingsDeltaDiagnosticCuda<Rng> {
+    type Error = CudaError;
+    fn next_element(&mut self, mut state: LatticeStateCuda<D>) -> Result<LatticeStateCuda<D>, CudaError> {
+        let (mut n_perf, mut n_acc, mut sum_p) = (0_i64, 0_i64, 0_f64);
+        check(unsafe {
+            ffi::lq_metropolis_hits(state.ctx.0, self.rng.next_u64(), self.rng.next_u64() >> 8, self.spread,
+                                    self.hits_per_call as i64, 0, &mut n_perf, &mut n_acc, &mut sum_p)
+        })?;
+        self.prob_replace_last = sum_p / (n_perf.max(1) as f64);
+        self.has_replace_last = n_acc > 0;
+        state.host_links = OnceLock::new();
+        Ok(state)
+    }
+}
+
+/// metropolis_hastings.rs:40-118 as a `MonteCarloDefault`: the proposal is a device clone with `number_of_update`
+/// random links multiplied by a matrix close to one; `McWrapper::new(MetropolisHastingsCuda::new(..)?, rng)` then
+/// accepts it on `probability_of_replacement` = exp(H_links(old) - H_links(new)) (monte_carlo/mod.rs:137-142), both
+/// energies being device reductions through `LatticeState::hamiltonian_links`.
+pub struct MetropolisHastingsCuda {
+    number_of_update: usize,
+    spread: Real,
+}
+impl MetropolisHastingsCuda {
+    pub fn new(number_of_update: usize, spread: Real) -> Option<Self> {
+        if number_of_update == 0 || spread <= 0_f64 || spread >= 1_f64 {
+            return None;
+        }
+        Some(Self { number_of_update, spread })
+    }
+}
+impl<const D: usize> lattice_qcd_rs::simulation::MonteCarloDefault<LatticeStateCuda<D>, D> for MetropolisHastingsCuda {
+    type Error = CudaError;
+    fn potential_next_element<Rng>(&mut self, state: &LatticeStateCuda<D>, rng: &mut Rng)
+                                   -> Result<LatticeStateCuda<D>, CudaError>
+    where
+        Rng: rand::Rng + ?Sized,
+    {
+        let mut new = state.clone();
+        let (mut n_perf, mut n_acc, mut sum_p) = (0_i64, 0_i64, 0_f64);
+        check(unsafe {
+            ffi::lq_metropolis_hits(new.ctx.0, rng.next_u64(), rng.next_u64() >> 8, self.spread,
+                                    self.number_of_update as i64, 1, &mut n_perf, &mut n_acc, &mut sum_p)
+        })?;
+        new.host_links = OnceLock::new();
+        Ok(new)
     }
 }

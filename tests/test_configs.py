@@ -222,3 +222,124 @@ def test_config5_largest_single_gpu_lattice():
     assert abs(c.hamiltonian_total() - h0) <= 1e-6 * abs(h0) and c.t == 3
     c.reunitarize()
     c.close()
+
+
+@pytest.mark.gpu
+def test_config3_full_size_matches_oracle():
+    """32^4 -- the size every bench number is quoted on -- CUDA against the oracle element-wise: plaquette / H_links,
+    the force, one fused MD step (lq_symplectic_n(dt, 1)), the Gauss field and one projection step, one heat-bath and
+    one over-relaxation sub-sweep pair, and the bulk-copy (TMA) upload / download round trip.  The tuned kernels' 32-bit
+    index arithmetic and the chunk layout at ext0 = 32 (one chunk per x0 row) are exercised only here.  About a minute
+    of oracle time on the box's host cores."""
+    import os
+    import torch
+    assert torch.cuda.is_available()
+    from lattice_qcd_rs_b200 import Context
+    n = 32
+    o = Oracle(4, n, a=1.0, beta=6.0)
+    o.set_num_threads(os.cpu_count() or 1)
+    c = Context(4, n, a=1.0, beta=6.0)
+    U = o.links_random(SEED_RNG)
+    E = o.momenta_refresh(SEED_RNG, 1)
+    c.links_upload(U)
+    c.efield_upload(E)
+    assert np.array_equal(c.links_download(), U) and np.array_equal(c.efield_download(), E)  # TMA row kernels: bit exact
+    ps = o.plaquette_sum(U)
+    assert abs(c.plaquette_sum() - ps) <= 1e-12 * abs(ps)
+    hl = o.hamiltonian_links(U)
+    assert abs(c.hamiltonian_links() - hl) <= 1e-12 * abs(hl)
+    he = o.hamiltonian_efield(E)
+    assert abs(c.hamiltonian_efield() - he) <= 1e-12 * abs(he)
+    assert rel(c.force(), o.force(U, literal=False)) <= 1e-12
+    # Gauss law: field, residual, one projection step
+    assert rel(c.gauss_field(), o.gauss_field(U, E)) <= 1e-12
+    gd = o.gauss_sum_div(U, E)
+    assert abs(c.gauss_sum_div() - gd) <= 1e-12 * gd
+    c.gauss_project_step()
+    assert rel(c.efield_download(), o.project_to_gauss_step(U, E)) <= 1e-12
+    # one fused MD step (kick dt/2, link step, kick dt/2)
+    c.efield_upload(E)
+    c.symplectic_n(0.01, 1)
+    Uo, Eo = o.integrate(U, E, "symplectic", 0.01, n=1, literal=False)
+    assert rel(c.links_download(), Uo) <= 1e-12 and rel(c.efield_download(), Eo) <= 1e-12
+    # local updates: a full heat-bath sweep and a full over-relaxation sweep against the oracle's checkerboard order
+    c.links_upload(U)
+    c.sweep_heatbath(SEED_RNG, 3)
+    assert rel(c.links_download(), o.sweep_heatbath(U, SEED_RNG, 3)) <= 1e-9
+    c.links_upload(U)
+    c.sweep_overrelax(0)
+    assert rel(c.links_download(), o.sweep_overrelax(U, 0)) <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------- config 2, README method
+def test_config2_single_link_hits_agree_with_sequential_reference(backend):
+    """MetropolisHastingsDeltaDiagnostic (metropolis_hastings.rs:374-417; the README example, README.md:47-80): batches
+    of independent random single-link hits on the device (lq_metropolis_hits) against the reference's own sequence of
+    single hits (oracle), 10^4 beta = 1 (6^4 on the CPU CI), matched hits per link, <Re Tr P>/3 within 2 sigma."""
+    name, ctx = backend
+    n = 10 if name == "cuda" else 6
+    o = Oracle(4, n, a=1000.0, beta=1.0)
+    c = ctx(4, n, a=1000.0, beta=1.0)
+    U0 = o.links_random(SEED_RNG)
+    therm, meas = 30, 30
+    U, ref = U0, []
+    for k in range(therm + meas):
+        for part in range(max(o.nl // 1000, 1)):
+            U, _, _ = o.metropolis_single_link(U, SEED_RNG + 1, k * 10000 + part, 0.1, min(1000, o.nl))
+            U = o.normalize_links(U)
+        if k >= therm:
+            ref.append(o.average_trace_plaquette(U).real / 3.0)
+    c.links_upload(U0)
+    got, perf_frac, acc = [], [], []
+    batch = o.nl // 16  # hits per call: an eighth of the links are in the call's (direction, colour) class
+    for k in range(therm + meas):
+        done = 0
+        part = 0
+        while done < o.nl:  # one "sweep" = Nl performed hits
+            n_perf, n_acc, sum_p = c.metropolis_hits(SEED_RNG + 2, k * 100000 + part, 0.1, batch)
+            assert 0 < n_perf <= batch and n_acc <= n_perf and 0.0 <= sum_p <= n_perf
+            perf_frac.append(n_perf / batch)
+            acc.append(n_acc / n_perf)
+            done += n_perf
+            part += 1
+        c.reunitarize()
+        if k >= therm:
+            got.append(c.average_trace_plaquette().real / 3.0)
+    ref, got = np.array(ref), np.array(got)
+    sig = np.hypot(ref.std(ddof=1) / np.sqrt(ref.size), got.std(ddof=1) / np.sqrt(got.size))
+    assert abs(ref.mean() - got.mean()) < 2.0 * 2.0 * sig, (ref.mean(), got.mean(), sig)
+    assert abs(got.mean() - 1.0 / 18.0) < 0.01
+    assert 0.5 < np.mean(acc) <= 1.0
+    # collisions inside a batch: n hits on m = Nl/8 links leave m (1 - exp(-n/m)) distinct ones: 1 - e^-0.5 = 0.787 of n
+    assert abs(np.mean(perf_frac) - (1.0 - np.exp(-0.5)) / 0.5) < 0.02
+
+
+def test_single_link_hit_is_the_reference_call(backend):
+    """n_hits = 1: one uniformly random link, same proposal and accept rule as delta_s_old_new_cmp; exactly one link
+    changes when the hit is accepted and none otherwise; force_accept applies the proposal unconditionally."""
+    name, ctx = backend
+    o = Oracle(4, 4, a=1.0, beta=6.0)
+    c = ctx(4, 4, a=1.0, beta=6.0)
+    U = o.links_random(SEED_RNG)
+    c.links_upload(U)
+    changed = 0
+    dirs = set()
+    for k in range(40):
+        before = c.links_download().copy()
+        n_perf, n_acc, sum_p = c.metropolis_hits(SEED_RNG, 1000 + k, 0.3, 1)
+        after = c.links_download()
+        diff = np.flatnonzero(np.abs(after - before).max(axis=1) > 0)
+        assert n_perf == 1 and n_acc in (0, 1) and 0.0 <= sum_p <= 1.0
+        assert diff.size == n_acc
+        if n_acc:
+            changed += 1
+            dirs.add(int(diff[0]) % 4)
+            # the accepted matrix is (an SU(3) matrix close to one) x (the old link): still unitary to rounding
+            m = to_c(after[diff])
+            assert np.abs(m @ np.conj(np.swapaxes(m, 1, 2)) - np.eye(3)).max() < 1e-12
+    assert 0 < changed < 40 and len(dirs) >= 3
+    before = c.links_download().copy()
+    n_perf, n_acc, _ = c.metropolis_hits(SEED_RNG, 5000, 0.3, 64, force_accept=True)
+    diff = np.flatnonzero(np.abs(c.links_download() - before).max(axis=1) > 0)
+    assert n_acc == n_perf == diff.size and 32 <= n_perf <= 64
+    assert len(set(int(i) % 4 for i in diff)) == 1  # one (direction, colour) class per call

@@ -150,6 +150,7 @@ def _check(res):
     (2, 4, [4, 4, 4, 8], [1, 1, 1, 2]),
     (4, 4, [4, 4, 4, 8], [1, 1, 2, 2]),
     (2, 3, [4, 6, 4], [1, 1, 2]),
+    (8, 4, [4, 4, 4, 8], [1, 1, 2, 4]),  # the process grid of the 8-GPU bench (z x t = 2 x 4, with corners)
 ])
 def test_decomposed_matches_oracle_gloo(world, D, gext, proc_grid):
     _check(_run(world, "gloo", D, gext, proc_grid))
@@ -170,3 +171,7 @@ def test_decomposed_matches_oracle_nccl():
             res = _run(4, "nccl", 4, [8, 8, 8, 8], [1, 1, 2, 2], transport)
             _check(res)
             assert res["transport"] == ("p2p" if transport == "p2p" else "nccl-callbacks"), res["transport"]
+        if n >= 8 and transport == "p2p":  # the 2(z) x 4(t) grid the 8-GPU bench runs on, incl. the zt corners
+            res = _run(8, "nccl", 4, [8, 8, 8, 16], [1, 1, 2, 4], transport)
+            _check(res)
+            assert res["transport"] == "p2p", res["transport"]

@@ -189,3 +189,111 @@ def test_omelyan_integrator_through_the_trait_surface(lib):
     plain2 = plain2.monte_carlo_step(hmc2)
     assert 0.0 <= hmc2.prob_replace_last() <= 1.0 and 0.0 <= p_om <= 1.0
     assert p_om >= hmc2.prob_replace_last() - 1e-12  # same momenta (same seed), smaller energy error
+
+
+def test_monte_carlo_default_and_wrapper(lib):
+    """MonteCarloDefault + McWrapper (monte_carlo/mod.rs:117-293, doc example :81-116): MetropolisHastingsDiagnostic
+    wrapped with a generator, stepped through LatticeState::monte_carlo_step on a cold 4^3 state at beta = 6."""
+    rng = lq.Rng(0)
+    assert lq.MetropolisHastingsDiagnostic.new(0, 0.1) is None and lq.MetropolisHastingsDiagnostic.new(1, 1.5) is None
+    mh = lq.MetropolisHastingsDiagnostic.new(1, 0.1)
+    wrapper = lq.McWrapper.new(mh, rng)
+    state = lq.LatticeStateDefault.new_cold(1.0, 6.0, 4, D=3, lib=lib)
+    h0 = state.hamiltonian_links()
+    assert h0 == 0.0
+    n_acc = 0
+    for _ in range(30):
+        old = state
+        state = state.monte_carlo_step(wrapper)
+        p = mh.prob_replace_last()
+        assert 0.0 <= p <= 1.0
+        if mh.has_replace_last():
+            n_acc += 1
+            assert state is not old
+            # probability_of_replacement is exp(H_old - H_new) clamped (monte_carlo/mod.rs:137-142)
+            want = min(1.0, np.exp(old.hamiltonian_links() - state.hamiltonian_links()))
+            assert abs(p - want) <= 1e-12
+        else:
+            assert state is old
+    assert 0 < n_acc <= 30 and state.hamiltonian_links() > 0.0
+    mcd, rng2 = wrapper.deconstruct()
+    assert mcd is mh and rng2 is rng and wrapper.mcd() is mh and wrapper.rng_mut() is rng
+
+
+def test_hybrid_method_couple(lib):
+    """HybridMethodCouple / Triple (hybrid.rs:330-446): methods applied in order, errors tagged with their position."""
+    rng = lq.Rng(SEED_RNG)
+    state = lq.LatticeStateDefault.new_determinist(1.0, 6.0, 4, rng, lib=lib)
+    hb = lq.HeatBathSweep.new(lq.Rng(1))
+    ov = lq.OverrelaxationSweepReverse.new()
+    couple = lq.HybridMethodCouple.new(hb, ov)
+    assert couple.method_1() is hb and couple.method_2() is ov and couple.deconstruct() == (hb, ov)
+    # same generator state => the couple equals the two calls made by hand
+    ref = state.clone()
+    ref = lq.HeatBathSweep.new(lq.Rng(1)).next_element(ref)
+    ref = ov.next_element(ref)
+    state = state.monte_carlo_step(couple)
+    assert np.array_equal(state.link_matrix(), ref.link_matrix())
+    triple = lq.HybridMethodTriple(hb, ov, lq.OverrelaxationSweepRotation.new())
+    h = state.hamiltonian_links()
+    state = triple.next_element(state)
+    assert np.isfinite(state.hamiltonian_links()) and state.hamiltonian_links() != h
+
+    class Boom(lq.MonteCarlo):
+        def next_element(self, state):
+            raise ValueError("boom")
+
+    with pytest.raises(lq.HybridMethodCoupleError) as e:
+        lq.HybridMethodCouple(Boom(), ov).next_element(state)
+    assert e.value.which == "ErrorFirst" and isinstance(e.value.error, ValueError)
+    with pytest.raises(lq.HybridMethodCoupleError) as e:
+        lq.HybridMethodCouple(ov, Boom()).next_element(state)
+    assert e.value.which == "ErrorSecond"
+
+
+def test_metropolis_hastings_delta_diagnostic_readme(lib):
+    """The README example (README.md:47-80; metropolis_hastings.rs:300-417) at a reduced size: 6^4 (README: 10^4),
+    beta = 1, a = 1000, spread 0.1, single random link hits with normalize_link_matrices in between, then
+    average_trace_plaquette().real() / 3.  One reference call = one hit; hits_per_call batches them on the device."""
+    assert lq.MetropolisHastingsDeltaDiagnostic.new(0.0, lq.Rng(1)) is None
+    assert lq.MetropolisHastingsDeltaDiagnostic.new(1.0, lq.Rng(1)) is None
+    rng = lq.Rng(SEED_RNG)
+    state = lq.LatticeStateDefault.new_determinist(1000.0, 1.0, 6, rng, lib=lib)
+    nl = state.lattice().number_of_canonical_links_space()
+    # the reference's call, one hit at a time
+    mh1 = lq.MetropolisHastingsDeltaDiagnostic.new(0.1, rng)
+    for _ in range(20):
+        state = state.monte_carlo_step(mh1)
+        assert mh1.hits_performed_last == 1 and 0.0 <= mh1.prob_replace_last() <= 1.0
+        assert mh1.has_replace_last() == (mh1.hits_accepted_last == 1)
+    # batched: ~40 hits per link in total
+    mh = lq.MetropolisHastingsDeltaDiagnostic.new(0.1, rng, hits_per_call=nl // 16)
+    vals = []
+    for k in range(40 * 16):
+        state = state.monte_carlo_step(mh)
+        if k % 16 == 15:
+            state.normalize_link_matrices()
+            if k >= 20 * 16:
+                vals.append(state.average_trace_plaquette().real / 3.0)
+    assert 0.5 < mh.prob_replace_last() <= 1.0
+    assert abs(np.mean(vals) - 1.0 / 18.0) < 0.01  # strong coupling: <P>/3 ~ beta/18
+
+
+def test_hmc_rejects_host_integrators(lib):
+    """a non-device integrator must not silently run whatever the context had selected."""
+    class HostIntegrator:
+        pass
+
+    rng = lq.Rng(3)
+    state = lq.LatticeStateDefault.new_determinist(1.0, 6.0, 4, rng, lib=lib)
+    with pytest.raises(TypeError):
+        lq.HybridMonteCarloDiagnostic.new(0.01, 2, HostIntegrator(), rng).next_element(state)
+    # an Omelyan trajectory leaves the context on the reference's integrator
+    hmc = lq.HybridMonteCarloDiagnostic.new(0.01, 2, lq.OmelyanCuda.new(), rng)
+    state = hmc.next_element(state)
+    ref = state.clone()
+    a = lq.LatticeStateEFSyncDefault.new_random_e_state(state, lq.Rng(9))
+    b = lq.LatticeStateEFSyncDefault.new_random_e_state(ref, lq.Rng(9))
+    a = a.simulate_symplectic_n(lq.SymplecticEulerCuda.new(), 0.01, 2)
+    b._touch().symplectic_n(0.01, 2)  # lq_symplectic_n directly: the reference's integrator
+    assert np.array_equal(a.link_matrix(), b.link_matrix())

@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "lq_geom_host.h"
-#include "lq_tuned.cuh"
+#include "lq_md_variants.cuh"
 
 #define CK(x)                                                                          \
   do {                                                                                 \
@@ -244,11 +244,11 @@ int main(int argc, char** argv) {
 #define V4(BLOCK, MINB)                                                                                            \
   vs.push_back({std::string("v4 lean nu-loop block=" #BLOCK " minb=" #MINB),                                        \
                 [&] {                                                                                               \
-                  lq_md4_kernel<BLOCK, MINB, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>(      \
+                  lq_md4x_kernel<BLOCK, MINB, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>(      \
                       g, U, U2, E, coef, dt / 2, dt, c_u, 2, nullptr, 0);                                             \
                   CK(cudaGetLastError());                                                                           \
                 },                                                                                                  \
-                (const void*)lq_md4_kernel<BLOCK, MINB, 1>, BLOCK})
+                (const void*)lq_md4x_kernel<BLOCK, MINB, 1>, BLOCK})
   V4(128, 3);
   V4(64, 6);
   V4(64, 7);
@@ -257,21 +257,21 @@ int main(int argc, char** argv) {
   vs.push_back({std::string("v4 block=" #BLOCK " minb=" #MINB " flags=" #FLAGS " carveout=" #CARVE),              \
                 [&] {                                                                                               \
                   if (CARVE >= 0)                                                                                   \
-                    cudaFuncSetAttribute(lq_md4_kernel<BLOCK, MINB, 1, FLAGS>,                                      \
+                    cudaFuncSetAttribute(lq_md4x_kernel<BLOCK, MINB, 1, FLAGS>,                                      \
                                          cudaFuncAttributePreferredSharedMemoryCarveout, CARVE);                   \
-                  lq_md4_kernel<BLOCK, MINB, 1, FLAGS><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>( \
+                  lq_md4x_kernel<BLOCK, MINB, 1, FLAGS><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>( \
                       g, U, U2, E, coef, dt / 2, dt, c_u, 2, nullptr, 0);                                             \
                   CK(cudaGetLastError());                                                                           \
                 },                                                                                                  \
-                (const void*)lq_md4_kernel<BLOCK, MINB, 1, FLAGS>, BLOCK})
+                (const void*)lq_md4x_kernel<BLOCK, MINB, 1, FLAGS>, BLOCK})
 #define V4P(BLOCK, MINB, FLAGS, GRID)                                                                              \
   vs.push_back({std::string("v4 persistent block=" #BLOCK " minb=" #MINB " flags=" #FLAGS " grid=" #GRID),        \
                 [&] {                                                                                               \
-                  lq_md4_kernel<BLOCK, MINB, 1, FLAGS><<<GRID, BLOCK>>>(g, U, U2, E, coef, dt / 2, dt, c_u, 2,     \
+                  lq_md4x_kernel<BLOCK, MINB, 1, FLAGS><<<GRID, BLOCK>>>(g, U, U2, E, coef, dt / 2, dt, c_u, 2,     \
                                                                        nullptr, 0);                                \
                   CK(cudaGetLastError());                                                                           \
                 },                                                                                                  \
-                (const void*)lq_md4_kernel<BLOCK, MINB, 1, FLAGS>, BLOCK})
+                (const void*)lq_md4x_kernel<BLOCK, MINB, 1, FLAGS>, BLOCK})
   V4P(128, 3, 18, 444);
   V4P(128, 3, 18, 888);
   V4P(128, 3, 18, 1776);
@@ -308,6 +308,20 @@ int main(int argc, char** argv) {
   V5(64, 6, 3);
   V5(64, 4, 3);
   V5(256, 1, 3);
+#define V6(BLOCK, MINB)                                                                                            \
+  vs.push_back({std::string("v6 product-pipelined block=" #BLOCK " minb=" #MINB),                                   \
+                [&] {                                                                                               \
+                  lq_md6_kernel<BLOCK, MINB, 1><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK>>>(      \
+                      g, U, U2, E, coef, dt / 2, dt, c_u, 2);                                                       \
+                  CK(cudaGetLastError());                                                                           \
+                },                                                                                                  \
+                (const void*)lq_md6_kernel<BLOCK, MINB, 1>, BLOCK})
+  V6(128, 3);
+  V6(128, 4);
+  V6(128, 5);
+  V6(64, 8);
+  V6(64, 10);
+  V6(256, 2);
 #define V2(MINB, MAP, GEOM, LABEL)                                                                           \
   vs.push_back({std::string("v2 nu-split block=384 minb=" #MINB " ") + LABEL,                                 \
                 [&, gg = GEOM] {                                                                              \
@@ -365,26 +379,25 @@ int main(int argc, char** argv) {
       int block;
     };
     std::vector<SV> sv;
-#define SW(BLOCK, MINB, KIND, PF)                                                                                  \
-  sv.push_back({std::string(KIND == 0 ? "heatbath" : "overrelax") + " block=" #BLOCK " minb=" #MINB " pf=" #PF,    \
+#define SW(BLOCK, MINB, KIND)                                                                                  \
+  sv.push_back({std::string(KIND == 0 ? "heatbath" : "overrelax") + " block=" #BLOCK " minb=" #MINB,    \
                 [&](int mu, int par) {                                                                              \
-                  lq_sweep4_kernel<BLOCK, MINB, KIND, PF><<<(unsigned)((g.vol / 2 + BLOCK - 1) / BLOCK), BLOCK>>>(  \
+                  lq_sweep4_kernel<BLOCK, MINB, KIND><<<(unsigned)((g.vol / 2 + BLOCK - 1) / BLOCK), BLOCK>>>(  \
                       g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);                                                    \
                   CK(cudaGetLastError());                                                                           \
                 },                                                                                                  \
-                (const void*)lq_sweep4_kernel<BLOCK, MINB, KIND, PF>, BLOCK})
-    SW(128, 3, 0, 0);
-    SW(128, 3, 0, 1);
-    SW(128, 4, 0, 0);
-    SW(128, 5, 0, 0);
-    SW(128, 6, 0, 0);
-    SW(64, 8, 0, 0);
-    SW(64, 10, 0, 0);
-    SW(256, 2, 0, 0);
-    SW(128, 3, 1, 0);
-    SW(128, 4, 1, 0);
-    SW(128, 5, 1, 0);
-    SW(128, 6, 1, 0);
+                (const void*)lq_sweep4_kernel<BLOCK, MINB, KIND>, BLOCK})
+    SW(128, 3, 0);
+    SW(128, 4, 0);
+    SW(128, 5, 0);
+    SW(128, 6, 0);
+    SW(64, 8, 0);
+    SW(64, 10, 0);
+    SW(256, 2, 0);
+    SW(128, 3, 1);
+    SW(128, 4, 1);
+    SW(128, 5, 1);
+    SW(128, 6, 1);
     printf("%-52s %5s %4s %9s %9s %10s\n", "sweep variant (8 sub-steps)", "regs", "occ", "ms/sweep", "GB/s(alg)", "maxdiff");
     for (size_t vi = 0; vi < sv.size(); ++vi) {
       auto& v = sv[vi];
@@ -397,7 +410,7 @@ int main(int argc, char** argv) {
       for (int mu = 0; mu < 4; ++mu)
         for (int par = 0; par < 2; ++par) v.run(mu, par);
       CK(cudaDeviceSynchronize());
-      const bool first_of_kind = v.name.find("minb=3 pf=0") != std::string::npos;
+      const bool first_of_kind = v.name.find("block=128 minb=3") != std::string::npos;
       CK(cudaMemcpy((first_of_kind ? hW0 : hW).data(), W, ub, cudaMemcpyDeviceToHost));
       double diff = 0;
       if (!first_of_kind)
