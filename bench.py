@@ -46,7 +46,7 @@ BETA, SPACING, DT, MD_STEPS = 6.0, 1.0, 0.01, 100
 TRAJ_COUNTER = 1  # momentum stream of THE trajectory every step repeats
 # Gauss-projection iterations of that trajectory on the 32^4 hot start (data dependent; bench.py prints the measured
 # count next to this constant, and the CPU arm derives its MD : Gauss mix from it)
-GAUSS_STEPS_PINNED = 173
+GAUSS_STEPS_PINNED = 101
 # algorithmic bytes per link of the dominant kernel (fused force + E kick + link step), DESIGN.md section 4:
 # read U 144 + read E 64 + write E 64 + write U' 144
 BYTES_FUSED = 416

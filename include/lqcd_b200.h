@@ -59,6 +59,9 @@ enum {
                                  field of the projected E, backward neighbours recomputed: 1376 instead of 2208
                                  B/site but 32 instead of 20 matrix products/site) instead of two passes.  Same
                                  results; measured slower on B200 (0.49 vs 0.43 ms at 32^4), so off by default */
+  LQ_FLAG_GAUSS_TWO_PASS = 32, /* lq_gauss_project: iterate with the two-pass kernels (Gauss field, then projection step:
+                                 2208 B/site) instead of the default D = 4 loop on the transported field U^+ E U (one
+                                 kernel per iteration, links read once, 1728 B/site); same results to 1e-15        */
   LQ_FLAG_UNIFORM_DIRECTION = 16 /* heat bath: draw the direction of the SU(2) vector uniformly on the sphere; default
                                  restates distribution.rs:199-219 as coded (a normalised Uniform(-1,1)^3 sample, which
                                  over-weights the cube diagonals).  With LQ_FLAG_PAULI3_FIXED and coupling_scale = 1/CA
@@ -213,13 +216,13 @@ int lq_halo_pack(lq_ctx*, int which, int dir, int side, void* d_buf, int64_t byt
 int lq_halo_unpack(lq_ctx*, int which, int dir, int side, const void* d_buf, int64_t bytes);
 int lq_halo_invalidate(lq_ctx*, int which);
 /* Peer-to-peer transport (preferred on one NVLink node): each rank exports CUDA-IPC handles of its field buffers
- * (7 x 64 bytes: U U2 E E2 G G2 flags), the caller all-gathers them and attaches the neighbours' handles; from then
+ * (9 x 64 bytes: U U2 E E2 G G2 T T2 flags), the caller all-gathers them and attaches the neighbours' handles; from then
  * on every ghost refresh is done by the library's own kernels writing the boundary slices straight into the
  * neighbours' ghost layers over NVLink, ordered by release/acquire flags in peer memory (no pack buffers, no NCCL,
  * no host round trip).  `offsets` = n_neighbors x D entries in {-1,0,+1}: the list must be identical on every rank
  * and closed under negation; peer_index[k] selects which of the n_peers opened handle sets neighbour k lives in
  * (two neighbours may be the same rank).  allreduce_sum of lq_set_comm is still used for the global sums. */
-int lq_p2p_export(lq_ctx*, void* handles_out, int64_t bytes /* 7 * 64 */);
+int lq_p2p_export(lq_ctx*, void* handles_out, int64_t bytes /* 9 * 64 */);
 int lq_p2p_attach(lq_ctx*, int n_peers, const void* peer_handles, int n_neighbors, const int* offsets,
                   const int* peer_index);
 int lq_p2p_enabled(const lq_ctx*);

@@ -25,6 +25,7 @@ ERRORS = {
 SYNC_SYNC, LEAP_LEAP, SYNC_LEAP, LEAP_SYNC, SYMPLECTIC = range(5)
 OR_ROTATION, OR_REVERSE, OR_SU2_SUBGROUPS = 0, 1, 2
 FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED, FLAG_GENERIC_KERNELS, FLAG_UNIFORM_DIRECTION = 1, 2, 4, 8, 16
+FLAG_GAUSS_TWO_PASS = 32
 INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_OMELYAN = 0, 1
 OMELYAN_LAMBDA = 0.1931833275037836  # second-order minimum-norm coefficient (Omelyan, Mryglod, Folk 2003)
 
@@ -514,12 +515,12 @@ class Context:
 
     # -- peer-to-peer transport
     def p2p_export(self):
-        buf = C.create_string_buffer(7 * 64)
-        self._check(self.lib.lq_p2p_export(self._h, buf, 7 * 64), "lq_p2p_export")
+        buf = C.create_string_buffer(9 * 64)
+        self._check(self.lib.lq_p2p_export(self._h, buf, 9 * 64), "lq_p2p_export")
         return buf.raw
 
     def p2p_attach(self, peer_handles, offsets, peer_index):
-        """peer_handles: list of 448-byte blobs (one per unique peer); offsets: list of D-vectors; peer_index: list."""
+        """peer_handles: list of 576-byte blobs (one per unique peer); offsets: list of D-vectors; peer_index: list."""
         blob = b"".join(peer_handles)
         n_nb = len(offsets)
         off = (C.c_int * (n_nb * self.D))(*[int(v) for o in offsets for v in o])

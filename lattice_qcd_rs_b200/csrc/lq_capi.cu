@@ -20,7 +20,7 @@
 
 #define LQ_BLOCK 128
 #define LQ_RBLOCK 256
-#define LQ_P2P_NBUF 7      /* U U2 E E2 G G2 flags */
+#define LQ_P2P_NBUF 9      /* U U2 E E2 G G2 T T2 flags */
 #define LQ_P2P_MAXNB 8     /* 3^2 - 1 neighbours of a 2-D process grid */
 #define LQ_P2P_HANDLE 64   /* sizeof(cudaIpcMemHandle_t) */
 #define LQ_PROF_CAP 8192     /* event pairs in flight; a full ring is drained into the per-class totals */
@@ -109,6 +109,7 @@ struct lq_ctx {
   bool even_extents;
   int odd_mask;  // bit d: ext[d] is odd (sweeps then use the colour classes of lq_site_class); 0 when all are even
   cx *U, *U2, *E, *E2, *G, *G2;
+  cx *T, *T2;  // transported field U^+ E U of the projection loop (lq_gausst4_kernel), D = 4 tuned path only
   cx *snapU, *snapE;
   cx* hmcU;  // reject-path copy of lq_hmc_trajectory (its own buffer: lq_snapshot / lq_restore keep theirs)
   int64_t snap_t;
@@ -126,7 +127,7 @@ struct lq_ctx {
   bool reduced_globally;  // the last reduce() result in h_result is already the global sum
   // peer-to-peer halo transport (CUDA IPC mappings of the neighbours' buffers, written over NVLink by our kernels)
   bool p2p_on;
-  cx* own[LQ_P2P_NBUF - 1];                       // the six field allocations in export order: U U2 E E2 G G2
+  cx* own[LQ_P2P_NBUF - 1];                       // the field allocations in export order: U U2 E E2 G G2 T T2
   unsigned long long* p2p_flags;                  // [LQ_P2P_MAXNB] incoming flags + [LQ_P2P_MAXNB] error word
   unsigned long long p2p_epoch;
   int p2p_nnb, p2p_npeers;
@@ -135,7 +136,7 @@ struct lq_ctx {
   int p2p_rev[LQ_P2P_MAXNB];                      // my slot in that neighbour's flag array
   void* p2p_base[LQ_P2P_MAXNB][LQ_P2P_NBUF];      // opened peer buffers (per unique peer)
   int64_t p2p_exchanges;
-  void* d_push;                                   // LqPush[6] on the device: peer table per link-buffer allocation
+  void* d_push;                                   // LqPush[8] on the device: peer table per field-buffer allocation
   // optional per-kernel-class CUDA-event timing (lq_profile_*)
   bool prof_on;
   int prof_n;                 // event pairs recorded since the last reset
@@ -148,6 +149,7 @@ struct lq_ctx {
   size_t u_bytes() const { return (size_t)g.nchunk * 32 * 9 * g.D * sizeof(cx); }
   size_t e_bytes() const { return (size_t)g.nchunk * 32 * 4 * g.D * sizeof(cx); }
   size_t g_bytes() const { return (size_t)g.nchunk * 32 * 9 * sizeof(cx); }
+  size_t t_bytes() const { return (size_t)g.nchunk * 32 * 5 * g.D * sizeof(cx); }
 };
 
 #ifndef LQ_HOST_EMU
@@ -542,6 +544,8 @@ int lq_ctx_destroy(lq_ctx* c) {
   rt_free(c->E2);
   rt_free(c->G);
   rt_free(c->G2);
+  rt_free(c->T);
+  rt_free(c->T2);
 #ifndef LQ_HOST_EMU
   for (int q = 0; q < c->p2p_npeers; ++q)
     for (int b = 0; b < LQ_P2P_NBUF; ++b)
@@ -1196,10 +1200,100 @@ int lq_gauss_project_step(lq_ctx* c) {
   c->g_valid = true;
   return LQ_OK;
 }
+#ifdef LQ_TUNED
+static int push_table_index(const lq_ctx* c, const cx* buf) {
+  for (int b = 0; b < LQ_P2P_NBUF - 1; ++b)
+    if (c->own[b] == buf) return b;
+  return -1;
+}
+// project_to_gauss (field.rs:1265-1294) on the transported field: T = U^+ E U once, then ONE kernel per iteration
+// (lq_gausst4_kernel: links read once, no Gauss-field array).  The residual of the state after steps 1, 5, 9, ... comes
+// out of the NEXT iteration's kernel (it forms G of its input anyway), which therefore runs speculatively: when the
+// check passes its output is simply not swapped in.
+static int gauss_project_transported(lq_ctx* c, int64_t max_steps, int64_t* steps_out) {
+  LQ_TRY(ensure_halo(c, 0));
+  LQ_TRY(ensure_halo(c, 1));
+  LQ_TRY(ensure_buf(&c->E2, c->e_bytes(), c));
+  LQ_TRY(ensure_buf(&c->T, c->t_bytes(), c));
+  LQ_TRY(ensure_buf(&c->T2, c->t_bytes(), c));
+  const bool push = c->p2p_on && c->d_push;
+  const int variant = (c->flags >> 6) & 3;  // A/B switch of the iteration kernel (bits 64, 128 of the flags)
+  const lq_i64 nb = lq_tuned_gausst_blocks(c->g, variant);
+  LQ_TRY(reduce_reserve(c, nb, 1));
+  const double thr = LQ_EPS * (double)(global_sites(c) * 4 * 8 * 10);  // field.rs:1285
+  auto table = [&](const cx* buf) -> const LqPush* {
+    if (!push) return nullptr;
+    const int bi = push_table_index(c, buf);
+    return bi < 0 ? nullptr : (const LqPush*)c->d_push + bi;
+  };
+  {
+    if (push) {
+      if (!table(c->T)) return LQ_E_COMM;
+      LQ_TRY(p2p_barrier(c));  // ready: nobody still reads the ghost layers of T
+    }
+    ProfScope ps(c, LQ_PROF_GAUSS_FIELD);
+    LQ_CHECK(lq_tuned_gauss_tinit(c->stream, c->g, c->U, c->E, c->T, table(c->T)));
+    c->launches++;
+  }
+  if (push) {
+    LQ_TRY(p2p_barrier(c));
+    c->p2p_exchanges++;
+  }
+  int64_t steps = 0;
+  int rc = LQ_OK;
+  for (;;) {
+    // the state after `steps` projection steps is in (E, T); check it when steps = 1, 5, 9, ...
+    const bool want_res = steps >= 1 && ((steps - 1) & 3) == 0;
+    if (push && (!table(c->E2) || !table(c->T2))) return LQ_E_COMM;
+    {
+      ProfScope ps(c, LQ_PROF_GAUSS_STEP);
+      LQ_CHECK(lq_tuned_gauss_titer(c->stream, c->g, c->U, c->E, c->T, c->E2, c->T2, c->d_partial, want_res, table(c->E2),
+                                    table(c->T2), variant));
+      c->launches++;
+    }
+    if (push) {
+      LQ_TRY(p2p_barrier(c));  // data (the ping-pong of the two buffer pairs makes a separate "ready" barrier unnecessary)
+      c->p2p_exchanges++;
+    }
+    if (want_res) {
+      ProfScope ps(c, LQ_PROF_GAUSS_DIV);
+      LQ_TRY(reduce_finish<1>(c, nb));
+      double v = c->h_result[0];
+      LQ_TRY(global_sum(c, &v, 1));
+      if (v != v) {
+        rc = LQ_E_GAUSS_DIVERGED;
+        break;
+      }
+      if (v <= thr) break;  // (E, T) is the projected state; the speculative step in (E2, T2) is dropped
+      if (steps >= max_steps) {
+        rc = LQ_E_GAUSS_DIVERGED;
+        break;
+      }
+    }
+    cx* t = c->E;
+    c->E = c->E2;
+    c->E2 = t;
+    t = c->T;
+    c->T = c->T2;
+    c->T2 = t;
+    ++steps;
+  }
+  c->halo_ok[1] = push;  // the pushes kept every ghost entry of E current
+  c->g_valid = false;
+  c->g_pp_safe = false;
+  if (steps_out) *steps_out = steps;
+  return rc;
+}
+#endif
 int lq_gauss_project(lq_ctx* c, int64_t max_steps, int64_t* steps_out) {
   if (!c) return LQ_E_BADARG;
   LQ_GUARD(c);
   if (max_steps <= 0) max_steps = 1 << 20;
+#ifdef LQ_TUNED
+  if (lq_tuned_ok(c->g) && !(c->flags & (LQ_FLAG_GENERIC_KERNELS | LQ_FLAG_GAUSS_FUSED | LQ_FLAG_GAUSS_TWO_PASS)) &&
+      (!c->decomposed || (c->p2p_on && c->d_push)))
+    return gauss_project_transported(c, max_steps, steps_out);
+#endif
   LQ_TRY(lq_gauss_project_step(c));
   int64_t steps = 1;
   const double thr = LQ_EPS * (double)(global_sites(c) * 4 * 8 * 10);  // field.rs:1285
@@ -1679,12 +1773,14 @@ int lq_p2p_export(lq_ctx* c, void* handles_out, int64_t bytes) {
   LQ_TRY(ensure_buf(&c->E2, c->e_bytes(), c));
   LQ_TRY(ensure_buf(&c->G, c->g_bytes(), c));
   LQ_TRY(ensure_buf(&c->G2, c->g_bytes(), c));
+  LQ_TRY(ensure_buf(&c->T, c->t_bytes(), c));
+  LQ_TRY(ensure_buf(&c->T2, c->t_bytes(), c));
   if (!c->p2p_flags) {
     LQ_TRY(rt_malloc((void**)&c->p2p_flags, 2 * LQ_P2P_MAXNB * sizeof(unsigned long long)));
     LQ_TRY(rt_memset(c->p2p_flags, 0, 2 * LQ_P2P_MAXNB * sizeof(unsigned long long), c->stream));
   }
   LQ_TRY(rt_sync(c->stream));
-  cx* bufs[LQ_P2P_NBUF - 1] = {c->U, c->U2, c->E, c->E2, c->G, c->G2};
+  cx* bufs[LQ_P2P_NBUF - 1] = {c->U, c->U2, c->E, c->E2, c->G, c->G2, c->T, c->T2};
   for (int b = 0; b < LQ_P2P_NBUF - 1; ++b) c->own[b] = bufs[b];
   static_assert(sizeof(cudaIpcMemHandle_t) == LQ_P2P_HANDLE, "IPC handle size");
   cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles_out;

@@ -395,6 +395,240 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Gauss projection loop without the Gauss-field round trip, D = 4 (project_to_gauss, field.rs:1265-1337).
+// The two-pass iteration (lq_gfield4_kernel + lq_gstep4_kernel) reads the links twice per iteration -- 2208 B/site --
+// although they do not change during the ~100 iterations of a projection.  Here every link carries, next to E_i(x),
+// its transported field  T_i(x) = U_i^+(x) E_i(x) U_i(x)  (Hermitian: stored as 3 real + 3 complex numbers in five
+// 16-byte planes), so that the Gauss field is a sum of stored quantities,
+//     G(x) = sum_j [ E_j(x) - T_j(x - j) ]                                               (field.rs:1174-1195)
+// and ONE kernel per iteration (one thread per site) forms G(x) and the four G(x + i) on the fly, applies the
+// projection step to the four links of the site (lq_gauss_project_link, field.rs:1301-1337) and writes E' and
+// T' = U^+ E' U: links read once, no G array -- 1728 B/site.  Same arithmetic and summation order as lq_gauss_site /
+// lq_gauss_project_link; the only difference from the two-pass path is that the anti-Hermitian rounding noise of
+// U^+ E U (1e-17 relative) is not carried (the lower triangle is the conjugate of the upper one).
+// RES: also reduce the residual sum_x |Tr((sum_a T_a) G(x))| (gauss_sum_div, field.rs:1199-1220) of the INPUT state
+// into per-block partial sums.  PUSH: E' and T' of boundary sites also go into the neighbour ranks' ghost layers.
+#define LQ_TPL 5 /* planes per link of the transported field: (h00, h11) (h22, 0) h01 h02 h12 */
+__device__ __forceinline__ M3 lq_herm_unpack(const cx* __restrict__ b) {
+  const cx q0 = __ldg(b), q1 = __ldg(b + 32), h01 = __ldg(b + 64), h02 = __ldg(b + 96), h12 = __ldg(b + 128);
+  M3 m;
+  m.e[0] = cmk(q0.x, 0.0);
+  m.e[4] = cmk(q0.y, 0.0);
+  m.e[8] = cmk(q1.x, 0.0);
+  m.e[1] = h01;
+  m.e[2] = h02;
+  m.e[5] = h12;
+  m.e[3] = cconj(h01);
+  m.e[6] = cconj(h02);
+  m.e[7] = cconj(h12);
+  return m;
+}
+__device__ __forceinline__ void lq_herm_pack(const M3& m, cx v[LQ_TPL]) {
+  v[0] = cmk(m.e[0].x, m.e[4].x);
+  v[1] = cmk(m.e[8].x, 0.0);
+  v[2] = m.e[1];
+  v[3] = m.e[2];
+  v[4] = m.e[5];
+}
+// G at the site of slot p from the stored fields; d[j] = slot delta to the site one step back in direction j
+__device__ __forceinline__ M3 lq_gauss_from_et(const cx* __restrict__ E, const cx* __restrict__ T, int p, int d0, int d1,
+                                               int d2, int d3) {
+  M3 acc = m3_zero();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const cx* eb = E + ((p >> 5) * 16 + j * 4) * 32 + (p & 31);
+    A8 e;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const cx v = __ldg(eb + k * 32);
+      e.e[2 * k] = v.x;
+      e.e[2 * k + 1] = v.y;
+    }
+    acc = m3_add(acc, lq_adjoint_to_matrix(e));
+    const int pj = p + (j == 0 ? d0 : j == 1 ? d1 : j == 2 ? d2 : d3);
+    acc = m3_sub(acc, lq_herm_unpack(T + ((pj >> 5) * (4 * LQ_TPL) + j * LQ_TPL) * 32 + (pj & 31)));
+  }
+  return acc;
+}
+// T = U^+ E U for every link (start of a projection loop)
+template <int BLOCK, int PUSH>
+__global__ void __launch_bounds__(BLOCK)
+    lq_gtinit4_kernel(LqGeom g, const cx* __restrict__ U, const cx* __restrict__ E, cx* __restrict__ T,
+                      const LqPush* __restrict__ psT) {
+  constexpr int SITES = BLOCK / 4;
+  const int mu = threadIdx.x / SITES;
+  const int n = blockIdx.x * SITES + (threadIdx.x - mu * SITES);
+  if (n >= (int)g.vol) return;
+  const LqSite4 s = lq_site4(g, n);
+  const int p = s.p;
+  const cx* eb = E + ((p >> 5) * 16 + mu * 4) * 32 + (p & 31);
+  A8 e;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const cx v = __ldg(eb + k * 32);
+    e.e[2 * k] = v.x;
+    e.e[2 * k + 1] = v.y;
+  }
+  const M3 u = lq_ld36(U, p, mu);
+  const M3 t = m3_mul_dn(u, lq_adjoint_to_matrix(e));  // U^+ E
+  M3 r = m3_zero();
+  m3_fma_nn(r, t, u);
+  cx tv[LQ_TPL];
+  lq_herm_pack(r, tv);
+  cx* tb = T + ((p >> 5) * (4 * LQ_TPL) + mu * LQ_TPL) * 32 + (p & 31);
+#pragma unroll
+  for (int k = 0; k < LQ_TPL; ++k) tb[k * 32] = tv[k];
+  if (PUSH) lq_push4<4 * LQ_TPL, LQ_TPL>(g, psT, s.x2, s.x3, p, mu * LQ_TPL, tv);
+}
+template <int BLOCK, int MINB, int PUSH, int RES, int UNR = 0>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_gausst4_kernel(LqGeom g, const cx* __restrict__ U, const cx* __restrict__ Ein, const cx* __restrict__ Tin,
+                      cx* __restrict__ Eout, cx* __restrict__ Tout, double* __restrict__ partial,
+                      const LqPush* __restrict__ psE, const LqPush* __restrict__ psT) {
+  const int n = blockIdx.x * BLOCK + threadIdx.x;
+  double res = 0.0;
+  if (n < (int)g.vol) {
+    const LqSite4 s = lq_site4(g, n);
+    const int p = s.p;
+    const M3 gx = lq_gauss_from_et(Ein, Tin, p, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
+    if (RES) {
+      cx tr[8];
+      lq_trace_gen(gx, tr);
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        re += tr[k].x;
+        im += tr[k].y;
+      }
+      res = sqrt(re * re + im * im);
+    }
+#pragma unroll UNR ? 4 : 1
+    for (int i = 0; i < 4; ++i) {
+      const int upi = lq_sel4(i, s.up[0], s.up[1], s.up[2], s.up[3]);
+      const int pp = p + upi;
+      // the site x + i steps back to x in direction i and has the deltas of x in the other directions
+      const M3 gp = lq_gauss_from_et(Ein, Tin, pp, i == 0 ? -upi : s.dn[0], i == 1 ? -upi : s.dn[1],
+                                     i == 2 ? -upi : s.dn[2], i == 3 ? -upi : s.dn[3]);
+      const int ee = ((p >> 5) * 16 + i * 4) * 32 + (p & 31);
+      A8 e;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const cx v = __ldg(Ein + ee + k * 32);
+        e.e[2 * k] = v.x;
+        e.e[2 * k + 1] = v.y;
+      }
+      const M3 u = lq_ld36(U, p, i);
+      e = lq_gauss_project_link(u, gx, gp, e);
+      cx ev[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ev[k] = cmk(e.e[2 * k], e.e[2 * k + 1]);
+        __stcs(Eout + ee + k * 32, ev[k]);
+      }
+      const M3 t = m3_mul_dn(u, lq_adjoint_to_matrix(e));  // U^+ E'
+      M3 r = m3_zero();
+      m3_fma_nn(r, t, u);
+      cx tv[LQ_TPL];
+      lq_herm_pack(r, tv);
+      cx* tb = Tout + ((p >> 5) * (4 * LQ_TPL) + i * LQ_TPL) * 32 + (p & 31);
+#pragma unroll
+      for (int k = 0; k < LQ_TPL; ++k) tb[k * 32] = tv[k];
+      if (PUSH) {
+        lq_push4<16, 4>(g, psE, s.x2, s.x3, p, i * 4, ev);
+        lq_push4<4 * LQ_TPL, LQ_TPL>(g, psT, s.x2, s.x3, p, i * LQ_TPL, tv);
+      }
+    }
+  }
+  if (RES) {
+    __shared__ double sm[BLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) res += __shfl_down_sync(0xffffffffu, res, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = res;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double x = 0.0;
+#pragma unroll
+      for (int w = 0; w < BLOCK / 32; ++w) x += sm[w];
+      partial[blockIdx.x] = x;
+    }
+  }
+}
+
+// the same iteration with one thread per LINK (four times the threads; G(x) is formed by each of the four threads of
+// a site): A/B variant of lq_gausst4_kernel, residual taken by the mu = 0 threads
+template <int BLOCK, int MINB, int PUSH, int RES>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_gausst4_link_kernel(LqGeom g, const cx* __restrict__ U, const cx* __restrict__ Ein, const cx* __restrict__ Tin,
+                           cx* __restrict__ Eout, cx* __restrict__ Tout, double* __restrict__ partial,
+                           const LqPush* __restrict__ psE, const LqPush* __restrict__ psT) {
+  constexpr int SITES = BLOCK / 4;
+  const int i = threadIdx.x / SITES;
+  const int n = blockIdx.x * SITES + (threadIdx.x - i * SITES);
+  double res = 0.0;
+  if (n < (int)g.vol) {
+    const LqSite4 s = lq_site4(g, n);
+    const int p = s.p;
+    const M3 gx = lq_gauss_from_et(Ein, Tin, p, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
+    if (RES && i == 0) {
+      cx tr[8];
+      lq_trace_gen(gx, tr);
+      double re = 0.0, im = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        re += tr[k].x;
+        im += tr[k].y;
+      }
+      res = sqrt(re * re + im * im);
+    }
+    const int upi = lq_sel4(i, s.up[0], s.up[1], s.up[2], s.up[3]);
+    const int pp = p + upi;
+    const M3 gp = lq_gauss_from_et(Ein, Tin, pp, i == 0 ? -upi : s.dn[0], i == 1 ? -upi : s.dn[1], i == 2 ? -upi : s.dn[2],
+                                   i == 3 ? -upi : s.dn[3]);
+    const int ee = ((p >> 5) * 16 + i * 4) * 32 + (p & 31);
+    A8 e;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const cx v = __ldg(Ein + ee + k * 32);
+      e.e[2 * k] = v.x;
+      e.e[2 * k + 1] = v.y;
+    }
+    const M3 u = lq_ld36(U, p, i);
+    e = lq_gauss_project_link(u, gx, gp, e);
+    cx ev[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ev[k] = cmk(e.e[2 * k], e.e[2 * k + 1]);
+      __stcs(Eout + ee + k * 32, ev[k]);
+    }
+    const M3 t = m3_mul_dn(u, lq_adjoint_to_matrix(e));
+    M3 r = m3_zero();
+    m3_fma_nn(r, t, u);
+    cx tv[LQ_TPL];
+    lq_herm_pack(r, tv);
+    cx* tb = Tout + ((p >> 5) * (4 * LQ_TPL) + i * LQ_TPL) * 32 + (p & 31);
+#pragma unroll
+    for (int k = 0; k < LQ_TPL; ++k) tb[k * 32] = tv[k];
+    if (PUSH) {
+      lq_push4<16, 4>(g, psE, s.x2, s.x3, p, i * 4, ev);
+      lq_push4<4 * LQ_TPL, LQ_TPL>(g, psT, s.x2, s.x3, p, i * LQ_TPL, tv);
+    }
+  }
+  if (RES) {
+    __shared__ double sm[BLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) res += __shfl_down_sync(0xffffffffu, res, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = res;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double x = 0.0;
+#pragma unroll
+      for (int w = 0; w < BLOCK / 32; ++w) x += sm[w];
+      partial[blockIdx.x] = x;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Metropolis sub-step (one direction, one colour), D = 4: MetropolisHastingsSweep (metropolis_hastings_sweep.rs:126-174)
 // with the lean addressing of lq_sweep4_kernel and the same arithmetic as KMetropolis (staple order nu ascending, up
 // then down; proposal draws, then the accept draw, from the link's Philox stream).  The block's (#accepted, sum of
@@ -649,6 +883,44 @@ static inline cudaError_t lq_tuned_gauss_step(cudaStream_t st, const LqGeom& g, 
   constexpr int BLOCK = 128;
   // 128 registers / 4 blocks per SM: 0.206 ms at 32^4; 166 / 3: 0.222; 96 / 5 (spills): 0.236; 80 / 6: 0.338
   lq_gstep4_kernel<BLOCK, 4><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, G, Ein, Eout);
+  return cudaGetLastError();
+}
+// projection loop on the transported field (lq_gausst4_kernel): T = U^+ E U, then one kernel per iteration
+static inline size_t lq_tuned_t_bytes(const LqGeom& g) { return (size_t)g.nchunk * 32 * 4 * LQ_TPL * sizeof(cx); }
+static inline cudaError_t lq_tuned_gauss_tinit(cudaStream_t st, const LqGeom& g, const cx* U, const cx* E, cx* T,
+                                               const LqPush* psT) {
+  constexpr int BLOCK = 128;
+  const unsigned nb = (unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4));
+  if (psT) lq_gtinit4_kernel<BLOCK, 1><<<nb, BLOCK, 0, st>>>(g, U, E, T, psT);
+  else lq_gtinit4_kernel<BLOCK, 0><<<nb, BLOCK, 0, st>>>(g, U, E, T, nullptr);
+  return cudaGetLastError();
+}
+// variant: 0 = one thread per site, rolled loop over the four links; 1 = the same, unrolled; 2 = one thread per link
+static inline lq_i64 lq_tuned_gausst_blocks(const LqGeom& g, int variant) {
+  (void)variant;
+  return (g.vol + 127) / 128;
+}
+template <int PUSH, int RES>
+static inline void lq_tuned_gauss_titer_launch(cudaStream_t st, const LqGeom& g, const cx* U, const cx* Ein, const cx* Tin,
+                                               cx* Eout, cx* Tout, double* partial, const LqPush* psE, const LqPush* psT,
+                                               int variant) {
+  constexpr int BLOCK = 128;
+  const unsigned nb = (unsigned)lq_tuned_gausst_blocks(g, variant);
+  if (variant == 2) lq_gausst4_kernel<BLOCK, 5, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT);
+  else if (variant == 1) lq_gausst4_kernel<BLOCK, 4, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT);
+  else if (variant == 3) lq_gausst4_kernel<BLOCK, 6, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT);
+  else lq_gausst4_kernel<BLOCK, 3, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT);
+}
+static inline cudaError_t lq_tuned_gauss_titer(cudaStream_t st, const LqGeom& g, const cx* U, const cx* Ein, const cx* Tin,
+                                               cx* Eout, cx* Tout, double* partial, bool want_res, const LqPush* psE,
+                                               const LqPush* psT, int variant) {
+  if (psE) {
+    if (want_res) lq_tuned_gauss_titer_launch<1, 1>(st, g, U, Ein, Tin, Eout, Tout, partial, psE, psT, variant);
+    else lq_tuned_gauss_titer_launch<1, 0>(st, g, U, Ein, Tin, Eout, Tout, partial, psE, psT, variant);
+  } else {
+    if (want_res) lq_tuned_gauss_titer_launch<0, 1>(st, g, U, Ein, Tin, Eout, Tout, partial, nullptr, nullptr, variant);
+    else lq_tuned_gauss_titer_launch<0, 0>(st, g, U, Ein, Tin, Eout, Tout, partial, nullptr, nullptr, variant);
+  }
   return cudaGetLastError();
 }
 static inline lq_i64 lq_tuned_metropolis_blocks(const LqGeom& g) { return (g.vol / 2 + 127) / 128; }

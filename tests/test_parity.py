@@ -366,12 +366,15 @@ def test_gauss_iteration_variants_agree(backend, ext):
     arithmetic in the same order: E, the Gauss field left behind and the iteration count must agree with each other
     (to the contraction choices of two different kernels) and with the oracle."""
     from lattice_qcd_rs_b200 import FLAG_GAUSS_FUSED
+    from lattice_qcd_rs_b200._capi import FLAG_GAUSS_TWO_PASS
     o = Oracle(4, ext, a=1.0, beta=6.0)
     U = hot(o)
     E = o.momenta_refresh(SEED_RNG, 9)
     Eo, ito = o.project_to_gauss(U, E)
     out = []
-    for flags in (0, FLAG_GAUSS_FUSED):
+    # 0: the default -- on the CUDA library lq_gauss_project iterates on the transported field U^+ E U (one kernel per
+    # iteration, lq_gausst4_kernel); TWO_PASS / FUSED: the two older iteration forms
+    for flags in (0, FLAG_GAUSS_TWO_PASS, FLAG_GAUSS_FUSED):
         c = backend(4, ext, a=1.0, beta=6.0)
         c.set_flags(flags)
         c.links_upload(U)
@@ -388,8 +391,9 @@ def test_gauss_iteration_variants_agree(backend, ext):
         assert rel(ef, Eo) <= 1e-10
         out.append((e1, g1, e3, g3, ef))
     assert rel(out[0][0], o.project_to_gauss_step(U, E)) <= RTOL
-    for a, b in zip(out[0], out[1]):
-        assert rel(a, b) <= 1e-13
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            assert rel(a, b) <= 1e-13
 
 
 @pytest.mark.parametrize("ext", [[8, 8, 8, 8], [4, 6, 2, 8], [32, 4, 4, 2]])
