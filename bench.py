@@ -18,7 +18,7 @@ free-running chain drifts and its Gauss iteration count climbs with the trajecto
 
 --config metric (default): 32^4 per GPU, weak scaling (split along t, and z at 8).   value / e2e as below.
 --config c4: BASELINE config 4, ONE 48^3 x 96 lattice strong-scaled over the N GPUs (t split; z too at 8).
---config c5: BASELINE config 5, 64^4 GLOBAL on N = 8 (2 x 32^4 per GPU); N < 8 runs 32^3 x (32 N)... see run_ours.
+--config c5: BASELINE config 5, ONE 64^4 lattice over the N GPUs (2 x 32^4 per GPU at N = 8).
 --config d3: BASELINE config 5b, the dimension-generic API on a D = 3 40^3 lattice (single GPU).
 
 value : device-resident (links stay in HBM between trajectories), CUDA events on the context stream, max over ranks.
@@ -268,7 +268,10 @@ def run_ours(args):
     else:
         gext_cfg = None
     parity = None
+    numa_node = None
     if world > 1:
+        from lattice_qcd_rs_b200.dist import bind_to_gpu_numa_node
+        numa_node = bind_to_gpu_numa_node(local)  # node-local pinned buffers for the e2e copies of the N ranks
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
         from lattice_qcd_rs_b200.dist import DistContext, proc_grid_for
@@ -448,7 +451,7 @@ def run_ours(args):
             "md_steps_per_trajectory": MD_STEPS,
             "gauss_projection_steps_per_trajectory": gauss_steps, "gauss_steps_each": traj["gauss_list"],
             "gauss_steps_pinned_constant": GAUSS_STEPS_PINNED, "accept_rate": traj["acc"] / max(traj["n"], 1),
-            "plaquette_over_3": plaq, "ghost_exchanges_per_step": exchanges,
+            "plaquette_over_3": plaq, "ghost_exchanges_per_step": exchanges, "rank0_numa_node": numa_node,
         },
         "md_only": {"value": md_only, "unit": "link-updates/s", "what": "lq_symplectic_n alone (no refresh/projection/H)"},
         "breakdown_ms_per_step": breakdown,

@@ -30,6 +30,33 @@ def proc_grid_for(D, world):
     return pg
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process (one rank per GPU) to the CPU cores of the NUMA node its GPU hangs off, so that the pinned host
+    buffers it allocates afterwards are node-local (first touch) and the eight ranks' host<->device copies do not all
+    cross the socket interconnect.  Returns the NUMA node, or None when the topology cannot be read (no change made)."""
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip().lower()
+        # nvidia-smi prints an 8-digit domain (00000000:1B:00.0); sysfs uses 4 digits
+        dom, rest = out.split(":", 1)
+        dev = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}"
+        node = int(open(dev + "/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001 -- an optimisation only
+        return None
+
+
 class DistContext:
     def __init__(self, D, global_extent, a=1.0, beta=1.0, CA=3.0, proc_grid=None, lib=None, device=None, group=None):
         assert dist.is_initialized(), "torch.distributed must be initialised (one process per GPU)"

@@ -256,5 +256,53 @@ int main(int argc, char** argv) {
            occ * v.block / 32, ms, 416.0 * nl / ms / 1e6, 3148.0 * nl / ms / 1e9, errE, errU);
     fflush(stdout);
   }
+  // ---- checkerboard sweep sub-steps (8 launches = one sweep)
+  {
+    cx* W;
+    CK(cudaMalloc(&W, ub));
+    struct SV {
+      std::string name;
+      std::function<void(int, int)> run;
+      const void* func;
+      int block;
+    };
+    std::vector<SV> sv;
+    const unsigned nbs = (unsigned)((g.vol / 2 + 127) / 128);
+#define SWV(NAME, KERN, ...)                                                                         \
+  sv.push_back({NAME, [&](int mu, int par) { KERN<<<nbs, 128>>>(__VA_ARGS__); CK(cudaGetLastError()); }, \
+                (const void*)KERN, 128})
+    SWV("heatbath  product kernel (pipelined staples)", (lq_sweep4_kernel<128, 3, 0>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
+    SWV("heatbath  rolled nu loop (round 1)", (lq_sweep4_rolled_kernel<128, 3, 0>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
+    SWV("overrelax product kernel (pipelined staples)", (lq_sweep4_kernel<128, 3, 1>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
+    SWV("overrelax rolled nu loop (round 1)", (lq_sweep4_rolled_kernel<128, 3, 1>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
+    SWV("overrelax su2-subgroups product kernel", (lq_sweep4_kernel<128, 3, 1>), g, W, mu, par, 0, 2, 6.0, 0x777ull, 5ull);
+    SWV("overrelax su2-subgroups rolled", (lq_sweep4_rolled_kernel<128, 3, 1>), g, W, mu, par, 0, 2, 6.0, 0x777ull, 5ull);
+    SWV("staple phase alone (pipelined, 168 regs)", (lq_sweep4_staples_only_kernel<128, 3, 1>), g, W, U2, mu, par);
+    SWV("staple phase alone (pipelined, 255 regs)", (lq_sweep4_staples_only_kernel<128, 2, 1>), g, W, U2, mu, par);
+    SWV("staple phase alone (pipelined, 128 regs)", (lq_sweep4_staples_only_kernel<128, 4, 1>), g, W, U2, mu, par);
+    printf("%-52s %5s %6s %4s %9s %9s\n", "sweep variant (8 sub-steps)", "regs", "local", "w/SM", "ms/sweep", "GB/s(alg)");
+    for (auto& v : sv) {
+      if (filter[0] && v.name.find(filter) == std::string::npos) continue;
+      cudaFuncAttributes at;
+      CK(cudaFuncGetAttributes(&at, v.func));
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.func, v.block, 0));
+      CK(cudaMemcpy(W, U, ub, cudaMemcpyDeviceToDevice));
+      for (int mu = 0; mu < 4; ++mu)
+        for (int par = 0; par < 2; ++par) v.run(mu, par);
+      CK(cudaEventRecord(e0));
+      for (int r = 0; r < reps; ++r)
+        for (int mu = 0; mu < 4; ++mu)
+          for (int par = 0; par < 2; ++par) v.run(mu, par);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      ms /= reps;
+      printf("%-52s %5d %6zu %4d %9.4f %9.1f\n", v.name.c_str(), at.numRegs, at.localSizeBytes, occ * v.block / 32, ms,
+             1296.0 * nl / ms / 1e6);
+      fflush(stdout);
+    }
+    CK(cudaFree(W));
+  }
   return 0;
 }

@@ -870,3 +870,67 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     for (int k = 0; k < 9; ++k) __stcs(bo + k * 32, un.e[k]);
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Sweep sub-step with the ROLLED nu loop of round 1 (A/B partner of lq_sweep4_kernel, whose staple sum is the
+// straight-line pipeline lq_staples4)
+template <int BLOCK, int MINB, int KIND>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_sweep4_rolled_kernel(LqGeom g, cx* __restrict__ U, int mu, int parity, int flags, int or_kind, double coupling,
+                            unsigned long long seed, unsigned long long counter) {
+  const int n = blockIdx.x * BLOCK + threadIdx.x;
+  if (n >= (int)(g.vol >> 1)) return;
+  lq_i64 gi;
+  const LqSite4 s = lq_site4_eo(g, n, parity, gi);
+  const int p = s.p;
+  const int pm = p + lq_sel4(mu, s.up[0], s.up[1], s.up[2], s.up[3]);
+  M3 acc = m3_zero();
+#pragma unroll 1
+  for (int j = 0; j < 3; ++j) {
+    const int nu = j + (j >= mu ? 1 : 0);
+    const int upn = lq_sel4(nu, s.up[0], s.up[1], s.up[2], s.up[3]), dnn = lq_sel4(nu, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
+    {
+      M3 a = lq_ld36(U, pm, nu);
+      M3 b = lq_ld36(U, p + upn, mu);
+      M3 t = m3_mul_nd(a, b);
+      M3 c = lq_ld36(U, p, nu);
+      m3_fma_nd(acc, t, c);
+    }
+    {
+      M3 a = lq_ld36(U, p + dnn, mu);
+      M3 b = lq_ld36(U, pm + dnn, nu);
+      M3 t = m3_mul_nn(a, b);
+      M3 c = lq_ld36(U, p + dnn, nu);
+      m3_fma_dn(acc, t, c);
+    }
+  }
+  cx* own = U + ((p >> 5) * 36 + mu * 9) * 32 + (p & 31);
+  M3 u;
+#pragma unroll
+  for (int kk = 0; kk < 9; ++kk) u.e[kk] = own[kk * 32];
+  M3 r;
+  if (KIND == 0) {
+    LqStream rng(seed, counter, (uint64_t)(gi * 4 + mu));
+    r = lq_heat_bath_link(u, acc, coupling, rng, flags);
+  } else {
+    r = lq_overrelax_link(u, acc, or_kind);
+  }
+#pragma unroll
+  for (int kk = 0; kk < 9; ++kk) own[kk * 32] = r.e[kk];
+}
+// staple phase ALONE (no rule; writes the staple sum over the own link: wrong on purpose, timing only): what a sweep
+// sub-step costs before the single-link rule
+template <int BLOCK, int MINB, int PIPE>
+__global__ void __launch_bounds__(BLOCK, MINB)
+    lq_sweep4_staples_only_kernel(LqGeom g, cx* __restrict__ U, cx* __restrict__ out, int mu, int parity) {
+  const int n = blockIdx.x * BLOCK + threadIdx.x;
+  if (n >= (int)(g.vol >> 1)) return;
+  lq_i64 gi;
+  const LqSite4 s = lq_site4_eo(g, n, parity, gi);
+  cx* own = U + ((s.p >> 5) * 36 + mu * 9) * 32 + (s.p & 31);
+  M3 acc, u;
+  lq_staples4(U, own, s, mu, acc, u);
+  cx* o = out + ((s.p >> 5) * 36 + mu * 9) * 32 + (s.p & 31);
+#pragma unroll
+  for (int kk = 0; kk < 9; ++kk) o[kk * 32] = cadd(acc.e[kk], u.e[kk]);
+}
