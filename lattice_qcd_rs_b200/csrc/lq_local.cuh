@@ -54,7 +54,7 @@ struct LqStream {
     buf[2] = r.z;
     buf[3] = r.w;
   }
-  LQ_HD uint64_t bits53() {
+  LQ_HD void words(uint32_t& hi, uint32_t& lo) {
     if (have == 0) {
       block();
       ctr[0] += 1;
@@ -62,12 +62,17 @@ struct LqStream {
     }
     int o = (2 - have) * 2;
     --have;
-    uint32_t hi = o == 0 ? buf[0] : buf[2];
-    uint32_t lo = o == 0 ? buf[1] : buf[3];
-    return ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+    hi = o == 0 ? buf[0] : buf[2];
+    lo = o == 0 ? buf[1] : buf[3];
   }
-  LQ_HD double uniform01() { return (double)bits53() * 0x1.0p-53; }            // [0,1)
-  LQ_HD double open_closed01() { return (double)(bits53() + 1) * 0x1.0p-53; }  // (0,1]
+  // 53-bit uniform  ((hi >> 5) * 2^26 + (lo >> 6)) * 2^-53  from two exact 32-bit conversions and one FMA (27 + 26 bits:
+  // every step is exact, so this IS the 64-bit integer conversion, without its multi-instruction device sequence)
+  LQ_HD double uniform01() {  // [0,1)
+    uint32_t hi, lo;
+    words(hi, lo);
+    return fma((double)(hi >> 5), 0x1.0p-27, (double)(lo >> 6) * 0x1.0p-53);
+  }
+  LQ_HD double open_closed01() { return uniform01() + 0x1.0p-53; }  // (0,1]: (bits + 1) * 2^-53, exactly
   LQ_HD double uniform_pm1() { return 2.0 * uniform01() - 1.0; }              // [-1,1)
   LQ_HD bool bernoulli(double p) { return uniform01() < p; }
   LQ_HD void normal_pair(double& z0, double& z1) {  // Box-Muller from one Philox block
@@ -295,8 +300,32 @@ LQ_HD M2 lq_heat_bath_su2(const M2& stap, double coupling, LqStream& rng, int fl
 // rows (ia, ib) of x * cur that the embedded 2x2 matrix x changes.  Every entry is the same k-ascending FMA chain as in
 // m3_mul_nn -- the skipped terms are products with the exact 0 / 1 entries of the embedding -- so the bits are those of
 // the two full 3x3 products (44 % of their FMAs).
-template <class Rule>
-LQ_HD M3 lq_subgroup_update(const M3& u, const M3& a, Rule rule) {
+// The staple sum `a` enters through an accessor: registers (LqStapleRegs) or, for the warp-specialised sweep kernel whose
+// rule warps run on a small register budget, the shared-memory slot the staple warps filled (LqStapleShared).
+struct LqStapleRegs {
+  const M3& a;
+  LQ_HD void cols(int which, cx ca[3], cx cb[3]) const {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ca[k] = which == 2 ? a.e[3 * k + 1] : a.e[3 * k];
+      cb[k] = which == 0 ? a.e[3 * k + 1] : a.e[3 * k + 2];
+    }
+  }
+};
+template <int STRIDE>
+struct LqStapleShared {
+  const cx* a;  // entry k of the 3x3 staple sum at a[k * STRIDE]
+  LQ_HD void cols(int which, cx ca[3], cx cb[3]) const {
+    const int c0 = which == 2 ? 1 : 0, c1 = which == 0 ? 1 : 2;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ca[k] = a[(3 * k + c0) * STRIDE];
+      cb[k] = a[(3 * k + c1) * STRIDE];
+    }
+  }
+};
+template <class Staple, class Rule>
+LQ_HD M3 lq_subgroup_update_acc(const M3& u, const Staple& a, Rule rule) {
   M3 cur = u;
 #pragma unroll 1
   for (int which = 0; which < 3; ++which) {
@@ -306,9 +335,8 @@ LQ_HD M3 lq_subgroup_update(const M3& u, const M3& a, Rule rule) {
     for (int k = 0; k < 3; ++k) {
       ra[k] = which == 2 ? cur.e[3 + k] : cur.e[k];
       rb[k] = which == 0 ? cur.e[3 + k] : cur.e[6 + k];
-      ca[k] = which == 2 ? a.e[3 * k + 1] : a.e[3 * k];
-      cb[k] = which == 0 ? a.e[3 * k + 1] : a.e[3 * k + 2];
     }
+    a.cols(which, ca, cb);
     M2 w;
     w.a = w.b = w.c = w.d = cmk(0.0, 0.0);
 #pragma unroll
@@ -332,6 +360,10 @@ LQ_HD M3 lq_subgroup_update(const M3& u, const M3& a, Rule rule) {
     }
   }
   return cur;
+}
+template <class Rule>
+LQ_HD M3 lq_subgroup_update(const M3& u, const M3& a, Rule rule) {
+  return lq_subgroup_update_acc(u, LqStapleRegs{a}, rule);
 }
 struct LqHeatBathRule {
   double coupling;

@@ -24,6 +24,38 @@ __device__ __forceinline__ M3 lq_ld36(const cx* __restrict__ U, int slot, int di
   for (int k = 0; k < 9; ++k) r.e[k] = __ldg(b + k * 32);
   return r;
 }
+// mbarrier / bulk-copy (TMA) primitives
+__device__ __forceinline__ unsigned lq_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lq_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lq_smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void lq_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lq_mbar_wait(unsigned long long* bar, unsigned phase) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(lq_smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void lq_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   lq_smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(lq_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void lq_bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(lq_smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 // site decode of the per-link kernels (row walk, even x0 first) and the slot deltas of the eight neighbours
 struct LqSite4 {
   int x0, x1, x2, x3;  // storage coordinates
@@ -745,37 +777,6 @@ __global__ void __launch_bounds__(192, MINB)
 // permutes it in shared memory (slot -> x0: even sites first; plane-major -> link-major; row-major 3x3 -> nalgebra's
 // column-major), and one bulk copy writes it out.  Global memory only ever sees full contiguous rows, where the
 // per-thread functors (KLinksToAos / KLinksFromAos) touch the AoS side in 16-byte pieces at a 144-byte stride.
-__device__ __forceinline__ unsigned lq_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void lq_mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lq_smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void lq_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lq_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void lq_mbar_wait(unsigned long long* bar, unsigned phase) {
-  unsigned ok;
-  do {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(ok)
-        : "r"(lq_smem_u32(bar)), "r"(phase)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void lq_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   lq_smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(lq_smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void lq_bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(lq_smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
 template <int TO_AOS>
 __global__ void __launch_bounds__(128)
     lq_aos4_tma_kernel(LqGeom g, cx* __restrict__ U, double* __restrict__ aos) {

@@ -223,6 +223,18 @@ int main(int argc, char** argv) {
   ADD("v9 fenced products <128,3> 168r", (lq_md9_kernel<128, 3, 1>), nb128, 128, g, U, U2, E, coef, dt / 2, dt, c_u, 2, 1);
   ADD("v9 fenced products <128,4> 128r", (lq_md9_kernel<128, 4, 1>), nb128, 128, g, U, U2, E, coef, dt / 2, dt, c_u, 2, 1);
   ADD("v9 fenced products <256,1> 255r", (lq_md9_kernel<256, 1, 1>), (nb128 + 1) / 2, 256, g, U, U2, E, coef, dt / 2, dt, c_u, 2, 1);
+  // V11: TMA-staged operands (persistent, one block per SM)
+  if (g.ext[0] == 32) {
+    int nsm11 = 148;
+    CK(cudaDeviceGetAttribute(&nsm11, cudaDevAttrMultiProcessorCount, 0));
+    const int ntiles11 = (int)(g.vol / 32);
+    CK(cudaFuncSetAttribute(lq_md11_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, LQ11_SMEM));
+    vs.push_back({"v11 TMA-staged operands, 8+1 warps, 1 block/SM", [=] {
+                    lq_md11_tma_kernel<1><<<nsm11, 288, LQ11_SMEM>>>(g, U, U2, E, coef, dt / 2, dt, c_u, 2, ntiles11);
+                    CK(cudaGetLastError());
+                  },
+                  (const void*)lq_md11_tma_kernel<1>, 288});
+  }
   ADD("v8 row split <384,1>", (lq_md8_rowsplit_kernel<1, 1>), nb128, 384, g, U, U2, E, coef, dt / 2, dt, c_u, 2);
   ADD("v8 row split <384,2>", (lq_md8_rowsplit_kernel<2, 1>), nb128, 384, g, U, U2, E, coef, dt / 2, dt, c_u, 2);
   ADD("v8 row split <384,3>", (lq_md8_rowsplit_kernel<3, 1>), nb128, 384, g, U, U2, E, coef, dt / 2, dt, c_u, 2);
@@ -265,31 +277,74 @@ int main(int argc, char** argv) {
       std::function<void(int, int)> run;
       const void* func;
       int block;
+      int family;  // 0 / 2 / 4: heat bath / SVD over-relaxation / SU(2) over-relaxation (+1: compared with the first)
+      int smem = 0;
     };
     std::vector<SV> sv;
     const unsigned nbs = (unsigned)((g.vol / 2 + 127) / 128);
-#define SWV(NAME, KERN, ...)                                                                         \
+#define SWV(NAME, FAM, KERN, ...)                                                                    \
   sv.push_back({NAME, [&](int mu, int par) { KERN<<<nbs, 128>>>(__VA_ARGS__); CK(cudaGetLastError()); }, \
-                (const void*)KERN, 128})
-    SWV("heatbath  product kernel (pipelined staples)", (lq_sweep4_kernel<128, 3, 0>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
-    SWV("heatbath  rolled nu loop (round 1)", (lq_sweep4_rolled_kernel<128, 3, 0>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
-    SWV("overrelax product kernel (pipelined staples)", (lq_sweep4_kernel<128, 3, 1>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
-    SWV("overrelax rolled nu loop (round 1)", (lq_sweep4_rolled_kernel<128, 3, 1>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
-    SWV("overrelax su2-subgroups product kernel", (lq_sweep4_kernel<128, 3, 1>), g, W, mu, par, 0, 2, 6.0, 0x777ull, 5ull);
-    SWV("overrelax su2-subgroups rolled", (lq_sweep4_rolled_kernel<128, 3, 1>), g, W, mu, par, 0, 2, 6.0, 0x777ull, 5ull);
-    SWV("staple phase alone (pipelined, 168 regs)", (lq_sweep4_staples_only_kernel<128, 3, 1>), g, W, U2, mu, par);
-    SWV("staple phase alone (pipelined, 255 regs)", (lq_sweep4_staples_only_kernel<128, 2, 1>), g, W, U2, mu, par);
-    SWV("staple phase alone (pipelined, 128 regs)", (lq_sweep4_staples_only_kernel<128, 4, 1>), g, W, U2, mu, par);
-    printf("%-52s %5s %6s %4s %9s %9s\n", "sweep variant (8 sub-steps)", "regs", "local", "w/SM", "ms/sweep", "GB/s(alg)");
+                (const void*)KERN, 128, FAM})
+    SWV("heatbath  product kernel (pipelined staples)", 0, (lq_sweep4_kernel<128, 3, 0>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
+    SWV("heatbath  rolled nu loop (round 1)", 1, (lq_sweep4_rolled_kernel<128, 3, 0>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
+    SWV("overrelax product kernel (pipelined staples)", 2, (lq_sweep4_kernel<128, 3, 1>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
+    SWV("overrelax rolled nu loop (round 1)", 3, (lq_sweep4_rolled_kernel<128, 3, 1>), g, W, mu, par, 0, 0, 6.0, 0x777ull, 5ull);
+    SWV("overrelax su2-subgroups product kernel", 4, (lq_sweep4_kernel<128, 3, 1>), g, W, mu, par, 0, 2, 6.0, 0x777ull, 5ull);
+    SWV("overrelax su2-subgroups rolled", 5, (lq_sweep4_rolled_kernel<128, 3, 1>), g, W, mu, par, 0, 2, 6.0, 0x777ull, 5ull);
+    SWV("staple phase alone (pipelined, 168 regs)", -1, (lq_sweep4_staples_only_kernel<128, 3, 1>), g, W, U2, mu, par);
+    SWV("staple phase alone (pipelined, 255 regs)", -1, (lq_sweep4_staples_only_kernel<128, 2, 1>), g, W, U2, mu, par);
+    SWV("staple phase alone (pipelined, 128 regs)", -1, (lq_sweep4_staples_only_kernel<128, 4, 1>), g, W, U2, mu, par);
+    // warp-specialised sub-step (staple warps + rule warps, persistent blocks): warp and register splits
+    int nsm = 148;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
+    const int ntasks = (int)((g.vol / 2 + 31) / 32);
+    const unsigned gws = (unsigned)(ntasks < nsm ? ntasks : nsm);
+#define SWS(NAME, KIND, NPW, NCW, PREG, CREG, ORK)                                                                   \
+  CK(cudaFuncSetAttribute(lq_sweep4ws_kernel<KIND, NPW, NCW, PREG, CREG>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                          LqWsCfg<NPW, NCW>::SMEM));                                                                   \
+  sv.push_back({NAME, [&](int mu, int par) {                                                                         \
+                  lq_sweep4ws_kernel<KIND, NPW, NCW, PREG, CREG><<<gws, LqWsCfg<NPW, NCW>::THREADS, LqWsCfg<NPW, NCW>::SMEM>>>( \
+                      g, W, mu, par, 0, ORK, 6.0, 0x777ull, 5ull, ntasks);                                           \
+                  CK(cudaGetLastError());                                                                            \
+                },                                                                                                   \
+                (const void*)lq_sweep4ws_kernel<KIND, NPW, NCW, PREG, CREG>, LqWsCfg<NPW, NCW>::THREADS,               \
+                KIND == 0 ? 0 : (ORK == 2 ? 4 : 2), LqWsCfg<NPW, NCW>::SMEM})
+    // register splits must balance: NPW (PREG - R0) <= NCW (R0 - CREG), R0 = the launch allocation (128 at 512 threads,
+    // 96 at 640): setmaxnreg.inc only draws from what the block's own warps released
+    SWS("heatbath  warp-spec. 8+8 warps 168/88", 0, 8, 8, 168, 88, 0);
+    SWS("heatbath  warp-spec. 8+8 warps 152/104", 0, 8, 8, 152, 104, 0);
+    SWS("heatbath  warp-spec. 12+8 warps 112/72", 0, 12, 8, 112, 72, 0);
+    SWS("heatbath  warp-spec. 12+8 warps 104/80", 0, 12, 8, 104, 80, 0);
+    SWS("heatbath  warp-spec. 12+4 warps 136/104", 0, 12, 4, 136, 104, 0);
+    SWS("heatbath  warp-spec. 12+4 warps 128/128", 0, 12, 4, 0, 0, 0);
+    SWS("overrelax warp-spec. 8+8 warps 128/128", 1, 8, 8, 0, 0, 0);
+    SWS("overrelax su2-subgroups warp-spec. 12+4 144/80", 1, 12, 4, 144, 80, 2);
+    SWS("overrelax su2-subgroups warp-spec. 8+8 168/88", 1, 8, 8, 168, 88, 2);
+    printf("%-52s %5s %6s %4s %9s %9s %9s\n", "sweep variant (8 sub-steps)", "regs", "local", "w/SM", "ms/sweep", "GB/s(alg)",
+           "max|dU|");
+    std::vector<double> hW(ub / 8), hR[3];
     for (auto& v : sv) {
-      if (filter[0] && v.name.find(filter) == std::string::npos) continue;
+      if (filter[0] && v.name.find(filter) == std::string::npos && v.name.find("product kernel") == std::string::npos) continue;
       cudaFuncAttributes at;
       CK(cudaFuncGetAttributes(&at, v.func));
       int occ = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.func, v.block, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v.func, v.block, v.smem));
       CK(cudaMemcpy(W, U, ub, cudaMemcpyDeviceToDevice));
       for (int mu = 0; mu < 4; ++mu)
         for (int par = 0; par < 2; ++par) v.run(mu, par);
+      CK(cudaDeviceSynchronize());
+      // one sweep from the common start: the first variant of a rule family is the reference of the ones after it
+      double dmax = -1.0;
+      if (v.family >= 0) {
+        CK(cudaMemcpy(hW.data(), W, ub, cudaMemcpyDeviceToHost));
+        const int f = v.family / 2;
+        if (v.family % 2 == 0 && hR[f].empty()) {
+          hR[f] = hW;
+        } else if (!hR[f].empty()) {
+          dmax = 0.0;
+          for (size_t i = 0; i < hW.size(); ++i) dmax = fmax(dmax, fabs(hW[i] - hR[f][i]));
+        }
+      }
       CK(cudaEventRecord(e0));
       for (int r = 0; r < reps; ++r)
         for (int mu = 0; mu < 4; ++mu)
@@ -298,8 +353,8 @@ int main(int argc, char** argv) {
       CK(cudaEventSynchronize(e1));
       CK(cudaEventElapsedTime(&ms, e0, e1));
       ms /= reps;
-      printf("%-52s %5d %6zu %4d %9.4f %9.1f\n", v.name.c_str(), at.numRegs, at.localSizeBytes, occ * v.block / 32, ms,
-             1296.0 * nl / ms / 1e6);
+      printf("%-52s %5d %6zu %4d %9.4f %9.1f %9.2e\n", v.name.c_str(), at.numRegs, at.localSizeBytes, occ * v.block / 32, ms,
+             1296.0 * nl / ms / 1e6, dmax);
       fflush(stdout);
     }
     CK(cudaFree(W));

@@ -934,3 +934,312 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 #pragma unroll
   for (int kk = 0; kk < 9; ++kk) o[kk * 32] = cadd(acc.e[kk], u.e[kk]);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// The same sub-step, WARP SPECIALISED: staple warps and rule warps of one persistent block run concurrently.
+// lq_sweep4_kernel serialises two very different phases in every thread -- the staple sum (HBM-bound, 168 registers,
+// 0.97 ms of a 1.47 ms heat-bath sweep at 32^4) and the single-link rule (scalar dependency chains: Philox rounds,
+// log, cospi, square roots; needs the link and a few temporaries) -- at the occupancy of the hungrier one, 3 warps per
+// scheduler.  Here the block is split: NPW staple warps compute the staple sums of 32-link tasks and hand (A, U) to
+// NCW rule warps through a ring of shared-memory slots (one mbarrier pair per slot: full / free; slot s % RING is
+// always written by staple warp s % NPW and read by rule warp s % NCW, so the schedule is static); a rule warp draws,
+// updates and stores the links of one task while the staple warps stream the next ones.  The register file is
+// re-partitioned at the start (setmaxnreg: PREG for the staple warps, CREG for the rule warps; setmaxnreg.inc only
+// draws from what the block's own warps released: NPW (PREG - R0) <= NCW (R0 - CREG), R0 = the launch allocation).
+// MEASURED AND REJECTED (profiles/r02n_kbench2_ws*.txt, 32^4, ms per heat-bath sweep; serial product kernel 1.476):
+//   block-wide named barriers, tiles of 256 links, 8 + 8 warps: 1.64 (152/104 registers) ... 1.77 (168/88);
+//   this mbarrier ring: 8 + 8 warps 2.19 - 2.41, 12 + 8 warps 2.60 - 2.82, 12 + 4 warps 2.66 - 3.16.
+// Why: the staple phase is limited by the bytes its warps keep in flight, and those live in registers -- the register
+// file is the prefetch buffer (staple phase alone: 0.97 / 1.04 / 1.12 ms at 12 x 168 / 8 x 244 / 16 x 128 registers,
+// i.e. whatever the split of the same 64 K registers).  Handing a third of the file to rule warps costs the staple
+// side more than the overlap returns; in the serial kernel the warps drift out of phase anyway, so staple and rule
+// phases of different warps already overlap.
+// Same arithmetic, order and random streams as lq_sweep4_kernel: bit-identical links.  Heat bath (KIND 0) and the
+// SU(2)-sub-group over-relaxation (KIND 1, or_kind 2) read the staple sum from the slot on demand (two columns per
+// sub-group); the SVD over-relaxations load it whole.
+__device__ __forceinline__ void lq_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+#define LQ_WS_SLOT (18 * 32) /* cx per slot: (A, U) of 32 links, entry k of lane l at [k * 32 + l] */
+template <int NPW, int NCW>
+struct LqWsCfg {
+  static constexpr int RING = (NPW == 12 && NCW == 8) ? 24 : (NPW == 8 && NCW == 8) ? 24 : (NPW == 12 && NCW == 4) ? 24 : 0;
+  static constexpr int THREADS = 32 * (NPW + NCW);
+  static constexpr int SMEM = RING * LQ_WS_SLOT * 16 + 2 * RING * 8;
+};
+// task of sequence number sq inside a block: groups of four adjacent tasks (eight x0 rows: their staples share
+// neighbour rows through L1) are dealt to the blocks round robin, so that all blocks work on the same region of the
+// lattice at the same time (L2 locality) and the tail is a fraction of one group per block
+template <int NPW>
+__device__ __forceinline__ int lq_ws_task(int sq) {
+  const int w = sq % NPW;
+  const int gs = (sq / NPW) * (NPW / 4) + (w >> 2);
+  return ((int)blockIdx.x + gs * (int)gridDim.x) * 4 + (w & 3);
+}
+template <int KIND, int NPW, int NCW, int PREG, int CREG>
+__global__ void __launch_bounds__(32 * (NPW + NCW), 1)
+    lq_sweep4ws_kernel(LqGeom g, cx* __restrict__ U, int mu, int parity, int flags, int or_kind, double coupling,
+                       unsigned long long seed, unsigned long long counter, int ntasks) {
+  constexpr int RING = LqWsCfg<NPW, NCW>::RING;
+  static_assert(RING > 0 && RING % NPW == 0 && RING % NCW == 0, "ring must pair staple and rule warps statically");
+  extern __shared__ __align__(16) unsigned char lq_ws_smem[];
+  cx* S = (cx*)lq_ws_smem;
+  unsigned long long* full = (unsigned long long*)(lq_ws_smem + RING * LQ_WS_SLOT * 16);
+  unsigned long long* empty = full + RING;
+  const int half = (int)(g.vol >> 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < RING) {
+    lq_mbar_init(&full[threadIdx.x], 32);
+    lq_mbar_init(&empty[threadIdx.x], 32);
+  }
+  __syncthreads();
+  if (warp < NPW) {
+    if (PREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PREG));
+    for (int sq = warp;; sq += NPW) {  // sq: sequence number of the task inside this block
+      const int task = lq_ws_task<NPW>(sq);
+      if (task >= ntasks) break;
+      const int slot = sq % RING, use = sq / RING;
+      if (use > 0) lq_mbar_wait(&empty[slot], (unsigned)(use - 1) & 1u);
+      const int n = task * 32 + lane;
+      if (n < half) {
+        lq_i64 gi;
+        const LqSite4 s = lq_site4_eo(g, n, parity, gi);
+        const cx* own = U + ((s.p >> 5) * 36 + mu * 9) * 32 + (s.p & 31);
+        M3 acc, u;
+        lq_staples4(U, own, s, mu, acc, u);
+        cx* d = S + slot * LQ_WS_SLOT + lane;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          d[k * 32] = acc.e[k];
+          d[(9 + k) * 32] = u.e[k];
+        }
+      }
+      lq_mbar_arrive(&full[slot]);
+    }
+  } else {
+    if (CREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CREG));
+    for (int sq = warp - NPW;; sq += NCW) {
+      const int task = lq_ws_task<NPW>(sq);
+      if (task >= ntasks) break;
+      const int slot = sq % RING, use = sq / RING;
+      lq_mbar_wait(&full[slot], (unsigned)use & 1u);
+      const int n = task * 32 + lane;
+      if (n < half) {
+        lq_i64 gi;
+        const LqSite4 s = lq_site4_eo(g, n, parity, gi);
+        cx* own = U + ((s.p >> 5) * 36 + mu * 9) * 32 + (s.p & 31);
+        const cx* a = S + slot * LQ_WS_SLOT + lane;
+        M3 u, r;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) u.e[k] = a[(9 + k) * 32];
+        if (KIND == 0) {
+          LqStream rng(seed, counter, (uint64_t)(gi * 4 + mu));
+          r = lq_subgroup_update_acc(u, LqStapleShared<32>{a}, LqHeatBathRule{coupling, &rng, flags});
+        } else if (or_kind == 2) {
+          r = lq_subgroup_update_acc(u, LqStapleShared<32>{a}, LqOverrelaxSu2Rule{});
+        } else {
+          M3 acc;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) acc.e[k] = a[k * 32];
+          r = lq_overrelax_link(u, acc, or_kind);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) own[kk * 32] = r.e[kk];
+      }
+      lq_mbar_arrive(&empty[slot]);
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// V11: the TMA-STAGED form north_star names -- neighbour links staged in shared memory by bulk asynchronous copies.
+// One persistent block per SM walks the x0 rows of the lattice (ext0 = 32: a row is one 32-slot chunk, so every
+// (row, direction) operand of the stencil is ONE contiguous 4608-byte block of the chunked-SoA layout; x0 shifts are
+// lane permutations inside a block).  A producer thread issues cp.async.bulk copies armed on mbarrier transaction
+// counts; eight consumer warps (direction mu x {up staples, down staples}) read their operands with LDS.128:
+//   * per row: the 4 own blocks (double buffered), then three ROUNDS, one per perfect matching of the directions --
+//     (0,1)(2,3), (0,2)(1,3), (0,3)(1,2).  In a round every direction's warps work on the plane shared with their
+//     partner, so both warps of a plane use the same neighbour blocks: 11 blocks per round (tools/gen_md11_tables.py),
+//     37 per row instead of the 76 operand fetches of the one-thread-per-link kernels (31 distinct blocks exist);
+//   * three stage buffers (one per round) + full / empty mbarriers: the producer runs up to a whole row ahead;
+//   * the down-staple warp hands its partial sum to the up-staple warp of the same direction through shared memory,
+//     which finishes the link (U A, trace, E kick, link step) as every other variant does.
+// Differences from the generic functor: the staples are summed in round order and as (up sum) + (down sum): errE / errU
+// are rounding-level, not zero.  Needs ext0 = 32 and no ghost layers (kbench lattices).
+#include "lq_md11_tables.inc"
+#define LQ11_BLK 288 /* cx per (row, direction) block: 9 planes x 32 slots */
+#define LQ11_SMEM ((2 * 4 + 3 * 11 + 4) * LQ11_BLK * 16 + 32 * 8)
+__device__ __forceinline__ unsigned lq_mbar_try(unsigned long long* bar, unsigned phase) {
+  unsigned ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok)
+      : "r"(lq_smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void lq_mbar_wait_wd(unsigned long long* bar, unsigned phase) {
+  if (lq_mbar_try(bar, phase)) return;
+  const long long t0 = clock64();
+  while (!lq_mbar_try(bar, phase))
+    if (clock64() - t0 > (1ll << 31)) __trap();  // ~1 s: a lost arrival must not hang the box
+}
+__device__ __forceinline__ M3 lq11_lds(const cx* blk, int ln) {
+  M3 r;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.e[k] = blk[k * 32 + ln];
+  return r;
+}
+// (9 warps put 3 on one SM sub-partition: 3 x 32 x registers <= 16 K caps the kernel at 168 registers per thread)
+template <int FUSED>
+__global__ void __launch_bounds__(288, 1)
+    lq_md11_tma_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef,
+                       double dt_e, double dt_u, double c_u, int nkick, int ntiles) {
+  extern __shared__ __align__(128) unsigned char lq11_smem[];
+  cx* own = (cx*)lq11_smem;                 // [2][4][288]
+  cx* stage = own + 2 * 4 * LQ11_BLK;       // [3][11][288]
+  cx* part = stage + 3 * 11 * LQ11_BLK;     // [4][288]
+  unsigned long long* bars = (unsigned long long*)(part + 4 * LQ11_BLK);
+  unsigned long long *ownfull = bars, *ownempty = bars + 2, *full = bars + 4, *empty = bars + 7, *partfull = bars + 10,
+                     *partempty = bars + 14;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      lq_mbar_init(&ownfull[i], 1);
+      lq_mbar_init(&ownempty[i], 8);
+    }
+    for (int i = 0; i < 3; ++i) {
+      lq_mbar_init(&full[i], 1);
+      lq_mbar_init(&empty[i], 8);
+    }
+    for (int i = 0; i < 4; ++i) {
+      lq_mbar_init(&partfull[i], 1);
+      lq_mbar_init(&partempty[i], 1);
+    }
+  }
+  __syncthreads();
+  const int e1 = g.ext[1], e2 = g.ext[2], e3 = g.ext[3];
+  if (warp == 8) {
+    // ---------------- producer warp: lane j < 11 issues stage block j of every round (its three row offsets and
+    // directions are loop invariants), lane 0 also arms the barriers and copies the 4 contiguous own blocks.
+    // (One thread issuing all 37 copies of a row, index arithmetic included, took ~3 us per row: 1.11 ms per launch.)
+    int o1[3], o2[3], o3[3], dd[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int j = lane < 11 ? lane : 0;
+      o1[r] = LQ11_OFF[r][j][0];
+      o2[r] = LQ11_OFF[r][j][1];
+      o3[r] = LQ11_OFF[r][j][2];
+      dd[r] = LQ11_DIR[r][j];
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int x1 = tile % e1, q = tile / e1, x2 = q % e2, x3 = q / e2;
+      const int tb = it & 1, k = it >> 1;
+      if (lane == 0) {
+        if (k >= 1) lq_mbar_wait_wd(&ownempty[tb], (unsigned)(k - 1) & 1u);
+        lq_mbar_expect_tx(&ownfull[tb], 4 * 4608);
+        lq_bulk_g2s(own + tb * 4 * LQ11_BLK, U + (lq_i64)tile * 36 * 32, 4 * 4608, &ownfull[tb]);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        int y1 = x1 + o1[r], y2 = x2 + o2[r], y3 = x3 + o3[r];
+        y1 = y1 < 0 ? y1 + e1 : (y1 >= e1 ? y1 - e1 : y1);
+        y2 = y2 < 0 ? y2 + e2 : (y2 >= e2 ? y2 - e2 : y2);
+        y3 = y3 < 0 ? y3 + e3 : (y3 >= e3 ? y3 - e3 : y3);
+        const lq_i64 ch = y1 + (lq_i64)e1 * (y2 + (lq_i64)e2 * y3);
+        if (lane == 0) {
+          if (it >= 1) lq_mbar_wait_wd(&empty[r], (unsigned)(it - 1) & 1u);
+          lq_mbar_expect_tx(&full[r], 11 * 4608);
+        }
+        __syncwarp();
+        if (lane < 11) lq_bulk_g2s(stage + (r * 11 + lane) * LQ11_BLK, U + (ch * 36 + dd[r] * 9) * 32, 4608, &full[r]);
+      }
+    }
+    return;
+  }
+  // ---------------- consumers: warp = mu + 4 * half (half 0: up staples + finish, half 1: down staples)
+  const int mu = warp & 3, half = warp >> 2;
+  const int x0 = lane < 16 ? 2 * lane : 2 * (lane - 16) + 1;
+  const int x0p = (x0 + 1) & 31, x0m = (x0 + 31) & 31;
+  const int lane_up = (x0p & 1) * 16 + (x0p >> 1), lane_dn = (x0m & 1) * 16 + (x0m >> 1);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int tb = it & 1;
+    cx ev[4];
+    const int ee = (tile * 16 + mu * 4) * 32 + lane;
+    if (half == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ev[k] = __ldcs(E + ee + k * 32);
+    }
+    lq_mbar_wait_wd(&ownfull[tb], (unsigned)(it >> 1) & 1u);
+    const cx* ownb = own + tb * 4 * LQ11_BLK;
+    M3 acc = m3_zero();
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      lq_mbar_wait_wd(&full[r], (unsigned)it & 1u);
+      const cx* sb = stage + r * 11 * LQ11_BLK;
+      M3 op[3];
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const int code = LQ11_OP[r][mu][half * 3 + o], sh = LQ11_SH[r][mu][half * 3 + o];
+        const cx* blk = code < 16 ? sb + code * LQ11_BLK : ownb + (code - 16) * LQ11_BLK;
+        op[o] = lq11_lds(blk, sh == 0 ? lane : (sh > 0 ? lane_up : lane_dn));
+      }
+      if (half == 0) {
+        const M3 t = m3_mul_nd(op[0], op[1]);
+        m3_fma_nd(acc, t, op[2]);
+      } else {
+        const M3 t = m3_mul_nn(op[0], op[1]);
+        m3_fma_dn(acc, t, op[2]);
+      }
+      __syncwarp();
+      if (lane == 0) lq_mbar_arrive(&empty[r]);
+    }
+    cx* pb = part + mu * LQ11_BLK;
+    if (half == 1) {
+      if (it >= 1) lq_mbar_wait_wd(&partempty[mu], (unsigned)(it - 1) & 1u);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) pb[k * 32 + lane] = acc.e[k];
+      __syncwarp();
+      if (lane == 0) {
+        lq_mbar_arrive(&partfull[mu]);
+        lq_mbar_arrive(&ownempty[tb]);
+      }
+      continue;
+    }
+    const M3 u = lq11_lds(ownb + mu * LQ11_BLK, lane);
+    __syncwarp();
+    if (lane == 0) lq_mbar_arrive(&ownempty[tb]);
+    lq_mbar_wait_wd(&partfull[mu], (unsigned)it & 1u);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const cx d = pb[k * 32 + lane];
+      acc.e[k] = cmk(acc.e[k].x + d.x, acc.e[k].y + d.y);
+    }
+    __syncwarp();
+    if (lane == 0) lq_mbar_arrive(&partempty[mu]);
+    M3 w = m3_mul_nn(u, acc);
+    cx tr[8];
+    lq_trace_gen(w, tr);
+    A8 e;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      e.e[2 * k] = ev[k].x;
+      e.e[2 * k + 1] = ev[k].y;
+    }
+    for (int kk = 0; kk < nkick; ++kk) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) e.e[k] = fma(coef * tr[k].y, dt_e, e.e[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(E + ee + k * 32, cmk(e.e[2 * k], e.e[2 * k + 1]));
+    if (FUSED) {
+      M3 un = lq_link_update<4>(u, e, dt_u, c_u, 0);
+      cx* bo = Unew + (tile * 36 + mu * 9) * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) __stcs(bo + k * 32, un.e[k]);
+    }
+  }
+}
