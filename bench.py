@@ -383,6 +383,13 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = MD_STEPS * nl_global * args.steps / (ms_e2e * 1e-3)
     bytes_links = nl_local * 18 * 8
+    # the host <-> device copies alone (upload + download of the links, all ranks at once): what separates e2e from value
+
+    def copy_step(i):
+        ctx.links_upload(hU)
+        ctx.links_download(out=hOut)
+
+    ms_copy = timed(copy_step, 3) / 3
 
     # ---------------- local-update sweeps of config 3 (secondary numbers)
     sweeps = {}
@@ -488,7 +495,10 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "link-updates/s", "h2d_bytes_per_step": bytes_links,
                 "d2h_bytes_per_step": bytes_links + 64, "ms_per_step": ms_e2e / args.steps,
-                "gauss_projection_steps_per_trajectory": e2e_state["gauss"] / max(args.steps, 1)},
+                "gauss_projection_steps_per_trajectory": e2e_state["gauss"] / max(args.steps, 1),
+                "host_copies_alone": {"ms_per_step": ms_copy, "gb_per_s_per_gpu_each_way": 2 * bytes_links / (ms_copy * 1e-3) / 1e9 / 2,
+                                      "what": "lq_links_upload + lq_links_download of the pinned host arrays on all ranks at "
+                                              "once, transposition kernels included, max over ranks"}},
         "gpu_launches": launches, "flags": args.flags,
         "clocks": clocks,
         "sweeps": sweeps,
