@@ -201,7 +201,7 @@ def dist_parity(world, pg):
     import torch.distributed as dist
     from lattice_qcd_rs_b200.dist import DistContext
     from oracle.oracle import Oracle
-    gext = [8, 8, 8, 8]
+    gext = [16, 8, 8, 8]  # x0 * x1 = 128 sites per (z, t) column: the kernels with the halo synchronisation folded in apply
     for d in range(4):
         gext[d] = max(gext[d], 4 * pg[d])
     o = Oracle(4, gext, a=SPACING, beta=BETA)
@@ -404,6 +404,17 @@ def run_ours(args):
             sweeps[name] = {"link_updates_per_s": nl_global * 3 / (t * 1e-3), "ms_per_sweep": t / 3,
                             "hbm_frac_algorithmic": (nl_global * 3 * 1296 / (t * 1e-3)) / 1e9 / peaks()[0]}
 
+    per_rank = None
+    if world > 1:
+        # per-rank averages of the two dominant kernels: the spread is the part of the multi-GPU loss that is GPU-to-GPU
+        # clock variation under the power cap (every ghost refresh waits for the slowest rank)
+        mine = torch.tensor([ms_fused / max(n_fused, 1), ms_gs / max(n_gs, 1)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"md_kernel_avg_ms": [float(t[0]) for t in allr], "gauss_iteration_avg_ms": [float(t[1]) for t in allr],
+                    "note": "each rank's own compute time (the waits for the neighbours sit in the barrier kernels between "
+                            "launches); with --flags 512 / 2560 (halo synchronisation folded into the kernels) a kernel's "
+                            "time includes its boundary blocks' wait"}
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -505,6 +516,8 @@ def run_ours(args):
     }
     if parity is not None:
         line["parity"] = parity
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)

@@ -62,6 +62,11 @@ enum {
   LQ_FLAG_GAUSS_TWO_PASS = 32, /* lq_gauss_project: iterate with the two-pass kernels (Gauss field, then projection step:
                                  2208 B/site) instead of the default D = 4 loop on the transported field U^+ E U (one
                                  kernel per iteration, links read once, 1728 B/site); same results to 1e-15        */
+  LQ_FLAG_FOLD_HALO_SYNC = 512, /* decomposed contexts with the peer-memory transport: fold the halo synchronisation of
+                                 the Gauss projection loop into its compute kernel (the last boundary block of a launch
+                                 releases the epoch, the boundary blocks of the next acquire it) instead of one barrier
+                                 kernel per ghost refresh; | 2048: the MD chain too; | 1024: its z faces scheduled
+                                 first.  Same results; measured SLOWER on 8 B200s (profiles/r02r-u), so off by default */
   LQ_FLAG_UNIFORM_DIRECTION = 16 /* heat bath: draw the direction of the SU(2) vector uniformly on the sphere; default
                                  restates distribution.rs:199-219 as coded (a normalised Uniform(-1,1)^3 sample, which
                                  over-weights the cube diagonals).  With LQ_FLAG_PAULI3_FIXED and coupling_scale = 1/CA

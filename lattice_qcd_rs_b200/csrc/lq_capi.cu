@@ -137,6 +137,8 @@ struct lq_ctx {
   void* p2p_base[LQ_P2P_MAXNB][LQ_P2P_NBUF];      // opened peer buffers (per unique peer)
   int64_t p2p_exchanges;
   void* d_push;                                   // LqPush[8] on the device: peer table per field-buffer allocation
+  unsigned int* d_fold_counter;                   // boundary blocks finished (halo synchronisation folded into the kernels)
+  bool p2p_pending;                               // the last folded launch released an epoch nobody has acquired yet
   // optional per-kernel-class CUDA-event timing (lq_profile_*)
   bool prof_on;
   int prof_n;                 // event pairs recorded since the last reset
@@ -371,6 +373,10 @@ static int p2p_exchange(lq_ctx* c, int which);
 static int p2p_barrier(lq_ctx* c);
 #endif
 static int ensure_halo(lq_ctx* c, int which) {
+#ifndef LQ_HOST_EMU
+  // a folded launch (LqFold) left its epoch for the next kernel of its chain to acquire; anybody else waits for it here
+  if (c->decomposed && c->p2p_pending) LQ_TRY(p2p_barrier(c));
+#endif
   if (!c->decomposed || c->halo_ok[which]) return LQ_OK;
   if (c->p2p_on) {
     LQ_TRY(p2p_exchange(c, which));
@@ -552,6 +558,7 @@ int lq_ctx_destroy(lq_ctx* c) {
       if (c->p2p_base[q][b]) cudaIpcCloseMemHandle(c->p2p_base[q][b]);
   rt_free(c->p2p_flags);
   rt_free(c->d_push);
+  rt_free(c->d_fold_counter);
 #endif
   rt_free(c->snapU);
   rt_free(c->snapE);
@@ -892,10 +899,30 @@ static int link_step(lq_ctx* c, const cx* Uin, cx* Uout, double dt, int use_exp)
   c->g_valid = false;
   return LQ_OK;
 }
+#ifdef LQ_TUNED
+// Schedule and epochs of a launch with the halo synchronisation folded in (lq_tuned.cuh: LqFold).  false: not applicable
+// (geometry, transport, or LQ_FLAG_FOLD_HALO_SYNC not set: the default) -- the caller keeps the barrier kernels.  The launch acquires the
+// epoch a preceding folded launch of the same chain released (p2p_pending) and releases the next one.
+static bool fold_fill(lq_ctx* c, int block_sites, int zfirst, LqFold& f) {
+  if (!c->p2p_on || !c->d_push || !c->d_fold_counter || !(c->flags & LQ_FLAG_FOLD_HALO_SYNC)) return false;
+  memset(&f, 0, sizeof(f));
+  if (!lq_fold_geom(c->g, block_sites, zfirst, f)) return false;
+  f.n = c->p2p_nnb;
+  for (int k = 0; k < c->p2p_nnb; ++k)
+    f.remote[k] = (unsigned long long*)c->p2p_base[c->p2p_peer[k]][LQ_P2P_NBUF - 1] + c->p2p_rev[k];
+  f.mine = c->p2p_flags;
+  f.counter = c->d_fold_counter;
+  f.wait_value = c->p2p_pending ? c->p2p_epoch : 0;
+  c->p2p_epoch += 1;
+  f.signal_value = c->p2p_epoch;
+  return true;
+}
+#endif
 // E += nkick * (dt_e F[U]);  U <- step(U, E_new, dt_u)  in one kernel (second link buffer, then swap)
 // chain: the previous operation on this context was the same fused step (inside one lq_symplectic_n / lq_md_n loop)
 static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u, int use_exp = 0, bool chain = false) {
-  LQ_TRY(ensure_halo(c, 0));
+  // inside a chain of folded launches the boundary blocks of this kernel acquire the previous step's epoch themselves
+  if (!(chain && c->p2p_pending)) LQ_TRY(ensure_halo(c, 0));
   LQ_TRY(ensure_buf(&c->U2, c->u_bytes(), c));
 #ifdef LQ_TUNED
   const bool tuned = lq_tuned_ok(c->g) && !(c->flags & LQ_FLAG_GENERIC_KERNELS);
@@ -910,6 +937,26 @@ static int efield_link_step(lq_ctx* c, double dt_e, int nkick, double dt_u, int 
     // previous one -- and a neighbour only arrived at the previous step's data barrier (which this rank has passed)
     // after that kernel had finished: one barrier per step is enough.
     if (!chain) LQ_TRY(p2p_barrier(c));
+    LqFold fold;
+    if ((c->flags & 2048) && fold_fill(c, 32, (c->flags & 1024) ? 1 : 0, fold)) {  // A/B bits (both measured slower): 2048 folds the MD chain too, 1024 schedules its z faces first
+      // the data barrier is folded in as well: the last boundary block releases this step's epoch, the boundary blocks of
+      // the next step (or the barrier in ensure_halo, when something else follows) acquire it
+      {
+        ProfScope ps2(c, LQ_PROF_EFIELD_LINK_STEP);
+        LQ_CHECK(lq_tuned_efield_link_step_fold(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u,
+                                                link_coef(c), nkick, (const LqPush*)c->d_push + bi, use_exp, fold));
+        c->launches++;
+      }
+      c->p2p_pending = true;
+      c->p2p_exchanges++;
+      cx* t = c->U;
+      c->U = c->U2;
+      c->U2 = t;
+      c->halo_ok[0] = true;
+      c->halo_ok[1] = false;
+      c->g_valid = false;
+      return LQ_OK;
+    }
     {
       ProfScope ps2(c, LQ_PROF_EFIELD_LINK_STEP);
       LQ_CHECK(lq_tuned_efield_link_step_push(c->stream, c->g, c->U, c->U2, c->E, force_coef(c), dt_e, dt_u,
@@ -1245,15 +1292,27 @@ static int gauss_project_transported(lq_ctx* c, int64_t max_steps, int64_t* step
     // the state after `steps` projection steps is in (E, T); check it when steps = 1, 5, 9, ...
     const bool want_res = steps >= 1 && ((steps - 1) & 3) == 0;
     if (push && (!table(c->E2) || !table(c->T2))) return LQ_E_COMM;
-    {
+    LqFold fold;
+    if (push && variant == 0 && fold_fill(c, 128, 1, fold)) {
+      // halo synchronisation inside the iteration kernel: its boundary blocks acquire the previous iteration's epoch and
+      // the last of them releases this one's
       ProfScope ps(c, LQ_PROF_GAUSS_STEP);
-      LQ_CHECK(lq_tuned_gauss_titer(c->stream, c->g, c->U, c->E, c->T, c->E2, c->T2, c->d_partial, want_res, table(c->E2),
-                                    table(c->T2), variant));
+      LQ_CHECK(lq_tuned_gauss_titer_fold(c->stream, c->g, c->U, c->E, c->T, c->E2, c->T2, c->d_partial, want_res,
+                                         table(c->E2), table(c->T2), fold));
       c->launches++;
-    }
-    if (push) {
-      LQ_TRY(p2p_barrier(c));  // data (the ping-pong of the two buffer pairs makes a separate "ready" barrier unnecessary)
+      c->p2p_pending = true;
       c->p2p_exchanges++;
+    } else {
+      {
+        ProfScope ps(c, LQ_PROF_GAUSS_STEP);
+        LQ_CHECK(lq_tuned_gauss_titer(c->stream, c->g, c->U, c->E, c->T, c->E2, c->T2, c->d_partial, want_res,
+                                      table(c->E2), table(c->T2), variant));
+        c->launches++;
+      }
+      if (push) {
+        LQ_TRY(p2p_barrier(c));  // data (the ping-pong of the two buffer pairs makes a separate "ready" barrier unnecessary)
+        c->p2p_exchanges++;
+      }
     }
     if (want_res) {
       ProfScope ps(c, LQ_PROF_GAUSS_DIV);
@@ -1693,6 +1752,7 @@ static int p2p_barrier(lq_ctx* c) {
   for (int k = 0; k < c->p2p_nnb; ++k)
     a.remote[k] = (unsigned long long*)c->p2p_base[c->p2p_peer[k]][LQ_P2P_NBUF - 1] + c->p2p_rev[k];
   c->p2p_epoch += 1;
+  c->p2p_pending = false;  // a full barrier is behind every epoch released before it
   lq_p2p_barrier_k<<<1, 32, 0, c->stream>>>(a, c->p2p_flags, c->p2p_epoch);
   c->launches++;
   LQ_CHECK(cudaGetLastError());
@@ -1839,6 +1899,10 @@ int lq_p2p_attach(lq_ctx* c, int n_peers, const void* peer_handles, int n_neighb
         tab[b].delta[k] = (int)delta;
         tab[b].nbmap[(D >= 3 ? c->p2p_off[k][D - 2] : 0) + 1][c->p2p_off[k][D - 1] + 1] = k;
       }
+    }
+    if (!c->d_fold_counter) {
+      LQ_TRY(rt_malloc((void**)&c->d_fold_counter, sizeof(unsigned int)));
+      LQ_TRY(rt_memset(c->d_fold_counter, 0, sizeof(unsigned int), c->stream));
     }
     if (!c->d_push) LQ_TRY(rt_malloc(&c->d_push, sizeof(tab)));
     LQ_TRY(rt_copy(c->d_push, tab, sizeof(tab), H2D, c->stream));

@@ -175,6 +175,111 @@ __device__ __forceinline__ void lq_push4(const LqGeom& g, const LqPush* __restri
     for (int kk = 0; kk < NV; ++kk) d[kk * 32] = v[kk];
   }
 }
+// ------------------------------------------------------------------------------------------------------------
+// Halo synchronisation folded into the compute kernels of a decomposed context (PUSH == 2).
+// A ghost refresh used to be  kernel (compute + push) -> barrier kernel (release my epoch to the neighbours, acquire
+// theirs) -> next kernel: 205 barrier launches per trajectory, each waiting for the slowest of the ranks.  Here the
+// producing kernel releases the epoch itself -- the LAST of its boundary blocks to finish (a device counter), after a
+// system-scope fence behind the pushes -- and the boundary blocks of the NEXT kernel acquire it before they touch a
+// ghost layer.  Only blocks of boundary columns (x2 or x3 on a split face) read ghosts or push, and the grid visits them
+// first, interleaved 1 : S with interior blocks: the epoch leaves after the first part of a kernel and is needed at the
+// start of the neighbours' next one, so a rank may run ahead of its neighbours by most of a kernel before it waits.
+// MEASURED ON 8 B200s (2 x 4 grid, 32^4 per GPU; profiles/r02r ... r02u, A/B on the same box) AND NOT THE DEFAULT: the
+// barrier launches disappear (unaccounted time per trajectory 6.0 -> 1.5 ms) but the MD kernel takes 0.805 - 0.84 ms on
+// every rank where the slowest rank's own compute is 0.745 ms (per-block system-scope fences behind NVLink stores and
+// acquire loads in 3968 boundary blocks per launch), 127 - 130 ms per trajectory against 122 - 124 ms with barrier
+// kernels; folding only the projection loop: 124.7 vs 122.2 ms.  Opt-in through LQ_FLAG_FOLD_HALO_SYNC.
+// One acquire covers both hazards of the ping-pong buffers: the neighbour's pushes into my ghosts have landed (RAW),
+// and its boundary blocks are done reading the ghosts this kernel's pushes overwrite (WAR).
+struct LqFold {
+  unsigned long long* remote[8];  // my slot in neighbour k's flag array (peer memory)
+  unsigned long long* mine;       // my flag array: slot k = neighbour k's epoch
+  unsigned int* counter;          // boundary blocks finished (zero between launches)
+  unsigned long long wait_value;  // epoch the boundary blocks acquire first (0: none)
+  unsigned long long signal_value;  // epoch released when the last boundary block is done (0: none)
+  int n;    // neighbours
+  int nB;   // boundary blocks of this launch (the last of them to finish releases the epoch)
+  int nF;   // boundary blocks scheduled first, one every S grid positions
+  int S;
+  int bpc;  // blocks per (x2, x3) column
+  int zfirst;  // 1: the z-face columns of the inner t-slices are scheduled first as well
+};
+// grid position -> natural block index (sites blk * BS ... in the reference order); isb: block of a boundary column.
+// The first f.nF blocks of the schedule (one every S grid positions) are boundary blocks: all of them (zfirst), or those
+// of the two boundary t-slices only -- the z faces then stay at their natural place in the sweep over x3, which keeps
+// ONE stream of x3 planes in L2 (pulling the z faces of all 30 inner slices forward cost the MD kernel 8 % on 8 GPUs).
+__device__ __forceinline__ int lq_fold_block(const LqGeom& g, const LqFold& f, int blk, bool& isb) {
+  const int e2 = g.ext[2], e3 = g.ext[3];
+  const int n3 = g.ghost[3] ? (e3 >= 2 ? 2 : 1) : 0;  // boundary values of x3, x2
+  const int n2 = g.ghost[2] ? (e2 >= 2 ? 2 : 1) : 0;
+  const int j = blk / f.S;
+  int col, within;
+  if (blk - j * f.S == 0 && j < f.nF) {
+    isb = true;
+    const int cb = j / f.bpc;
+    within = j - cb * f.bpc;
+    const int p1 = n3 * e2;  // columns of the boundary t-slices come first, then (zfirst) the z faces of the other slices
+    int x2, x3;
+    if (cb < p1) {
+      const int q = cb / e2;
+      x3 = q == 0 ? 0 : e3 - 1;
+      x2 = cb - q * e2;
+    } else {
+      const int r = cb - p1, q = r / n2;
+      x3 = (n3 ? 1 : 0) + q;
+      x2 = r - q * n2 == 0 ? 0 : e2 - 1;
+    }
+    col = x2 + e2 * x3;
+  } else {
+    const int ji = blk - min((blk + f.S - 1) / f.S, f.nF);
+    const int ci = ji / f.bpc;
+    within = ji - ci * f.bpc;
+    if (f.zfirst) {  // the rest: interior columns
+      isb = false;
+      const int i2 = e2 - n2, q = ci / i2;
+      col = (n2 ? 1 : 0) + (ci - q * i2) + e2 * ((n3 ? 1 : 0) + q);
+    } else {  // the rest: every column of the inner t-slices, z faces included
+      const int q = ci / e2, x2 = ci - q * e2;
+      isb = n2 && (x2 == 0 || x2 == e2 - 1);
+      col = x2 + e2 * ((n3 ? 1 : 0) + q);
+    }
+  }
+  return col * f.bpc + within;
+}
+__device__ __forceinline__ void lq_fold_wait(const LqFold& f) {  // all threads of a boundary block
+  if (f.wait_value == 0) return;
+  if ((int)threadIdx.x < f.n) {
+    const long long t0 = clock64();
+    unsigned long long v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f.mine + threadIdx.x) : "memory");
+      if (v >= f.wait_value) break;
+      if (*(volatile unsigned long long*)(f.mine + 8) != 0) break;  // an earlier wait gave up: do not pile up timeouts
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s
+        f.mine[8] = f.wait_value;  // error latch (LQ_P2P_MAXNB), reported by the next reduction / lq_sync
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void lq_fold_signal(const LqFold& f) {  // all threads of a boundary block, after their pushes
+  if (f.signal_value == 0) return;
+  // one system-scope fence per block, behind the barrier that orders the other threads' pushes before it (a fence in
+  // every thread made each boundary block wait for its own NVLink round trips: +0.09 ms per MD launch on 8 GPUs)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(f.counter, 1u) + 1u == (unsigned)f.nB) {
+      atomicExch(f.counter, 0u);
+      __threadfence_system();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // static indices: the parameter struct stays in the constant bank
+        if (k < f.n) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.remote[k]), "l"(f.signal_value) : "memory");
+    }
+  }
+}
 // Fused force + E kick (+ link step into Unew when FUSED; USE_EXP: U <- exp(i dt E) U instead of the Euler rule).
 // The staple sum is a chain of twelve 3x3 products,  t = a b^+, acc += t c^+  (up)  and  t = a b, acc += t^+ c  (down)
 // for nu ascending (the order of lq_staple_sum: same bits as the generic functor), written as STRAIGHT-LINE code with
@@ -259,10 +364,18 @@ __device__ __forceinline__ void lq_md4_body(const LqGeom& g, const cx* __restric
 template <int BLOCK, int MINB, int FUSED, int USE_EXP = 0, int PUSH = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
     lq_md4_kernel(LqGeom g, const cx* __restrict__ U, cx* __restrict__ Unew, cx* __restrict__ E, double coef, double dt_e,
-                  double dt_u, double c_u, int nkick, const LqPush* __restrict__ ps, int bps) {
+                  double dt_u, double c_u, int nkick, const LqPush* __restrict__ ps, int bps, const LqFold fold) {
   // ps: device-resident peer table, read by the threads of boundary slices only; bps: blocks per t-slice (0: keep
-  // the natural block order)
+  // the natural block order); PUSH == 2: boundary columns first, halo synchronisation inside the kernel (LqFold)
   int blk = blockIdx.x;
+  if (PUSH == 2) {
+    bool isb;
+    blk = lq_fold_block(g, fold, blk, isb);
+    if (isb) lq_fold_wait(fold);
+    lq_md4_body<BLOCK, FUSED, USE_EXP, 1>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, ps, blk);
+    if (isb) lq_fold_signal(fold);
+    return;
+  }
   if (PUSH && bps) {
     // The blocks of the two boundary t-slices are interleaved 1 : (S-1) with interior blocks over the first part of
     // the grid: their NVLink stores are spread over S times their own compute time instead of saturating the link
@@ -516,8 +629,14 @@ template <int BLOCK, int MINB, int PUSH, int RES, int UNR = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
     lq_gausst4_kernel(LqGeom g, const cx* __restrict__ U, const cx* __restrict__ Ein, const cx* __restrict__ Tin,
                       cx* __restrict__ Eout, cx* __restrict__ Tout, double* __restrict__ partial,
-                      const LqPush* __restrict__ psE, const LqPush* __restrict__ psT) {
-  const int n = blockIdx.x * BLOCK + threadIdx.x;
+                      const LqPush* __restrict__ psE, const LqPush* __restrict__ psT, const LqFold fold) {
+  int blk = blockIdx.x;
+  bool isb = false;
+  if (PUSH == 2) {  // boundary columns first, halo synchronisation inside the kernel (see LqFold)
+    blk = lq_fold_block(g, fold, blk, isb);
+    if (isb) lq_fold_wait(fold);
+  }
+  const int n = blk * BLOCK + threadIdx.x;
   double res = 0.0;
   if (n < (int)g.vol) {
     const LqSite4 s = lq_site4(g, n);
@@ -581,9 +700,10 @@ __global__ void __launch_bounds__(BLOCK, MINB)
       double x = 0.0;
 #pragma unroll
       for (int w = 0; w < BLOCK / 32; ++w) x += sm[w];
-      partial[blockIdx.x] = x;
+      partial[blk] = x;  // natural block order: the final sum does not depend on the visiting order
     }
   }
+  if (PUSH == 2 && isb) lq_fold_signal(fold);
 }
 
 // the same iteration with one thread per LINK (four times the threads; G(x) is formed by each of the four threads of
@@ -829,7 +949,7 @@ static inline cudaError_t lq_tuned_efield_step(cudaStream_t st, const LqGeom& g,
                                                int nkick) {
   constexpr int BLOCK = 128;
   lq_md4_kernel<BLOCK, 3, 0><<<(unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4)), BLOCK, 0, st>>>(g, U, nullptr, E, coef, dt,
-                                                                                                0.0, 0.0, nkick, nullptr, 0);
+                                                                                                0.0, 0.0, nkick, nullptr, 0, LqFold{});
   return cudaGetLastError();
 }
 static inline cudaError_t lq_tuned_efield_link_step(cudaStream_t st, const LqGeom& g, const cx* U, cx* Unew, cx* E,
@@ -838,9 +958,9 @@ static inline cudaError_t lq_tuned_efield_link_step(cudaStream_t st, const LqGeo
   constexpr int BLOCK = 128;
   const unsigned nb = (unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4));
   if (use_exp)
-    lq_md4_kernel<BLOCK, 3, 1, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0);
+    lq_md4_kernel<BLOCK, 3, 1, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0, LqFold{});
   else
-    lq_md4_kernel<BLOCK, 3, 1, 0><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0);
+    lq_md4_kernel<BLOCK, 3, 1, 0><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, nullptr, 0, LqFold{});
   return cudaGetLastError();
 }
 static inline cudaError_t lq_tuned_sweep(cudaStream_t st, const LqGeom& g, cx* U, int kind /*0 hb, 1 or*/, int mu, int parity,
@@ -907,10 +1027,10 @@ static inline void lq_tuned_gauss_titer_launch(cudaStream_t st, const LqGeom& g,
                                                int variant) {
   constexpr int BLOCK = 128;
   const unsigned nb = (unsigned)lq_tuned_gausst_blocks(g, variant);
-  if (variant == 2) lq_gausst4_kernel<BLOCK, 5, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT);
-  else if (variant == 1) lq_gausst4_kernel<BLOCK, 4, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT);
-  else if (variant == 3) lq_gausst4_kernel<BLOCK, 6, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT);
-  else lq_gausst4_kernel<BLOCK, 3, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT);
+  if (variant == 2) lq_gausst4_kernel<BLOCK, 5, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, LqFold{});
+  else if (variant == 1) lq_gausst4_kernel<BLOCK, 4, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, LqFold{});
+  else if (variant == 3) lq_gausst4_kernel<BLOCK, 6, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, LqFold{});
+  else lq_gausst4_kernel<BLOCK, 3, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, LqFold{});
 }
 static inline cudaError_t lq_tuned_gauss_titer(cudaStream_t st, const LqGeom& g, const cx* U, const cx* Ein, const cx* Tin,
                                                cx* Eout, cx* Tout, double* partial, bool want_res, const LqPush* psE,
@@ -949,9 +1069,52 @@ static inline cudaError_t lq_tuned_efield_link_step_push(cudaStream_t st, const 
   const int bps = (g.ghost[3] && slice % (BLOCK / 4) == 0) ? (int)(slice / (BLOCK / 4)) : 0;
   const unsigned nb = (unsigned)((g.vol + BLOCK / 4 - 1) / (BLOCK / 4));
   if (use_exp)
-    lq_md4_kernel<BLOCK, 3, 1, 1, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
+    lq_md4_kernel<BLOCK, 3, 1, 1, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps, LqFold{});
   else
-    lq_md4_kernel<BLOCK, 3, 1, 0, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps);
+    lq_md4_kernel<BLOCK, 3, 1, 0, 1><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, bps, LqFold{});
+  return cudaGetLastError();
+}
+
+// ---- launches with the halo synchronisation folded in (PUSH == 2).  lq_fold_geom fills the block schedule of a kernel
+// whose blocks hold `bs` consecutive sites; false: the geometry is not covered (blocks would straddle (x2, x3) columns)
+static inline bool lq_fold_geom(const LqGeom& g, int bs, int zfirst, LqFold& f) {
+  if (g.D != 4 || (!g.ghost[2] && !g.ghost[3]) || g.ghost[0] || g.ghost[1]) return false;
+  const lq_i64 colsites = (lq_i64)g.ext[0] * g.ext[1];
+  if (colsites % bs != 0 || g.vol % bs != 0) return false;
+  const int e2 = g.ext[2], e3 = g.ext[3];
+  const int n3 = g.ghost[3] ? (e3 >= 2 ? 2 : 1) : 0, n2 = g.ghost[2] ? (e2 >= 2 ? 2 : 1) : 0;
+  const lq_i64 colB = (lq_i64)n3 * e2 + (lq_i64)(e3 - n3) * n2;
+  const lq_i64 bpc = colsites / bs, total = (lq_i64)e2 * e3 * bpc, nB = colB * bpc;
+  if (nB <= 0 || nB > total || total > 0x7fffffff) return false;
+  f.bpc = (int)bpc;
+  f.nB = (int)nB;
+  f.zfirst = (zfirst || n3 == 0) ? 1 : 0;  // no t split: the z faces are all there is to schedule first
+  const lq_i64 nF = f.zfirst ? nB : (lq_i64)n3 * e2 * bpc;
+  f.nF = (int)nF;
+  const lq_i64 sp = total / nF;
+  f.S = (int)(sp < 1 ? 1 : (sp > 4 ? 4 : sp));
+  return true;
+}
+static inline cudaError_t lq_tuned_efield_link_step_fold(cudaStream_t st, const LqGeom& g, const cx* U, cx* Unew, cx* E,
+                                                         double coef, double dt_e, double dt_u, double c_u, int nkick,
+                                                         const LqPush* d_ps, int use_exp, const LqFold& fold) {
+  constexpr int BLOCK = 128;
+  const unsigned nb = (unsigned)(g.vol / (BLOCK / 4));
+  if (use_exp)
+    lq_md4_kernel<BLOCK, 3, 1, 1, 2><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, 0, fold);
+  else
+    lq_md4_kernel<BLOCK, 3, 1, 0, 2><<<nb, BLOCK, 0, st>>>(g, U, Unew, E, coef, dt_e, dt_u, c_u, nkick, d_ps, 0, fold);
+  return cudaGetLastError();
+}
+static inline cudaError_t lq_tuned_gauss_titer_fold(cudaStream_t st, const LqGeom& g, const cx* U, const cx* Ein,
+                                                    const cx* Tin, cx* Eout, cx* Tout, double* partial, bool want_res,
+                                                    const LqPush* psE, const LqPush* psT, const LqFold& fold) {
+  constexpr int BLOCK = 128;
+  const unsigned nb = (unsigned)(g.vol / BLOCK);
+  if (want_res)
+    lq_gausst4_kernel<BLOCK, 3, 2, 1, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, fold);
+  else
+    lq_gausst4_kernel<BLOCK, 3, 2, 0, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, fold);
   return cudaGetLastError();
 }
 

@@ -208,7 +208,7 @@ int main(int argc, char** argv) {
 #define ADD(NAME, KERN, GRID, BLOCK, ...)                                                  \
   vs.push_back({NAME, [&] { KERN<<<GRID, BLOCK>>>(__VA_ARGS__); CK(cudaGetLastError()); }, \
                 (const void*)KERN, BLOCK})
-  ADD("md4 product kernel <128,3>", (lq_md4_kernel<128, 3, 1>), nb128, 128, g, U, U2, E, coef, dt / 2, dt, c_u, 2, nullptr, 0);
+  ADD("md4 product kernel <128,3>", (lq_md4_kernel<128, 3, 1>), nb128, 128, g, U, U2, E, coef, dt / 2, dt, c_u, 2, nullptr, 0, LqFold{});
   ADD("v7 straight-line pipeline <128,3> 168r", (lq_md7_kernel<128, 3, 1>), nb128, 128, g, U, U2, E, coef, dt / 2, dt, c_u, 2);
   ADD("v7 straight-line pipeline <128,4> 128r", (lq_md7_kernel<128, 4, 1>), nb128, 128, g, U, U2, E, coef, dt / 2, dt, c_u, 2);
   ADD("v7 straight-line pipeline <128,5>  96r", (lq_md7_kernel<128, 5, 1>), nb128, 128, g, U, U2, E, coef, dt / 2, dt, c_u, 2);

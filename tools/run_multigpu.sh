@@ -9,10 +9,10 @@ for cfg in $CFGS; do
   steps=5; [ "$cfg" != metric ] && steps=3
   out=gpurun_out/${TAG}_bench_${cfg}_${N}gpu
   if [ "$N" = 1 ]; then
-    timeout 300 python bench.py --config $cfg --steps $steps --warmup 3 > $out.json 2> $out.err
+    timeout 300 python bench.py --config $cfg --steps $steps --warmup 3 $BENCH_EXTRA > $out.json 2> $out.err
   else
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) \
-      bench.py --gpus $N --config $cfg --steps $steps --warmup 3 > $out.json 2> $out.err
+      bench.py --gpus $N --config $cfg --steps $steps --warmup 3 $BENCH_EXTRA > $out.json 2> $out.err
   fi
   echo "== $cfg N=$N rc=$?"; head -c 400 $out.json; echo; tail -2 $out.err
 done
