@@ -4,6 +4,8 @@
 // both); what changes is the mapping of threads to links, the register budget and the memory-level parallelism.
 // Variants that were measured and not adopted live in tools/lq_md_variants.cuh (kbench only).
 #pragma once
+#include <cstdlib>
+
 #include "lq_kernels.cuh"
 
 #ifndef LQ_HOST_EMU
@@ -625,7 +627,11 @@ __global__ void __launch_bounds__(BLOCK)
   for (int k = 0; k < LQ_TPL; ++k) tb[k * 32] = tv[k];
   if (PUSH) lq_push4<4 * LQ_TPL, LQ_TPL>(g, psT, s.x2, s.x3, p, mu * LQ_TPL, tv);
 }
-template <int BLOCK, int MINB, int PUSH, int RES, int UNR = 0>
+// SH: the Gauss fields G(x) the threads of a block form for their own sites are passed through shared memory to the
+// threads that need them as G(x + 0) (same x0 row: always inside the block) and G(x + 1) (the next row: three rows of
+// four) -- the same bits, formed once instead of twice: 63 of the 232 128-bit loads of a thread and their additions go.
+// Needs ext0 = 32 (a row = a warp), ext1 and the volume multiples of the block (the launcher checks).
+template <int BLOCK, int MINB, int PUSH, int RES, int UNR = 0, int SH = 0>
 __global__ void __launch_bounds__(BLOCK, MINB)
     lq_gausst4_kernel(LqGeom g, const cx* __restrict__ U, const cx* __restrict__ Ein, const cx* __restrict__ Tin,
                       cx* __restrict__ Eout, cx* __restrict__ Tout, double* __restrict__ partial,
@@ -638,10 +644,16 @@ __global__ void __launch_bounds__(BLOCK, MINB)
   }
   const int n = blk * BLOCK + threadIdx.x;
   double res = 0.0;
+  __shared__ cx gsm[SH ? 9 * BLOCK : 1];
   if (n < (int)g.vol) {
     const LqSite4 s = lq_site4(g, n);
     const int p = s.p;
     const M3 gx = lq_gauss_from_et(Ein, Tin, p, s.dn[0], s.dn[1], s.dn[2], s.dn[3]);
+    if (SH) {  // (the volume is a multiple of the block: every thread gets here)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) gsm[k * BLOCK + threadIdx.x] = gx.e[k];
+      __syncthreads();
+    }
     if (RES) {
       cx tr[8];
       lq_trace_gen(gx, tr);
@@ -657,9 +669,23 @@ __global__ void __launch_bounds__(BLOCK, MINB)
     for (int i = 0; i < 4; ++i) {
       const int upi = lq_sel4(i, s.up[0], s.up[1], s.up[2], s.up[3]);
       const int pp = p + upi;
-      // the site x + i steps back to x in direction i and has the deltas of x in the other directions
-      const M3 gp = lq_gauss_from_et(Ein, Tin, pp, i == 0 ? -upi : s.dn[0], i == 1 ? -upi : s.dn[1],
-                                     i == 2 ? -upi : s.dn[2], i == 3 ? -upi : s.dn[3]);
+      M3 gp;
+      // thread of the block that holds x + i: the x0 neighbour inside the warp's row, or the same lane one row up
+      int src = -1;
+      if (SH && i == 0) {
+        const int x0p = s.x0 + 1 < 32 ? s.x0 + 1 : 0;
+        src = (threadIdx.x & ~31) + (x0p & 1) * 16 + (x0p >> 1);
+      } else if (SH && i == 1 && threadIdx.x + 32 < BLOCK) {
+        src = threadIdx.x + 32;
+      }
+      if (src >= 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) gp.e[k] = gsm[k * BLOCK + src];
+      } else {
+        // the site x + i steps back to x in direction i and has the deltas of x in the other directions
+        gp = lq_gauss_from_et(Ein, Tin, pp, i == 0 ? -upi : s.dn[0], i == 1 ? -upi : s.dn[1], i == 2 ? -upi : s.dn[2],
+                              i == 3 ? -upi : s.dn[3]);
+      }
       const int ee = ((p >> 5) * 16 + i * 4) * 32 + (p & 31);
       A8 e;
 #pragma unroll
@@ -1021,6 +1047,12 @@ static inline lq_i64 lq_tuned_gausst_blocks(const LqGeom& g, int variant) {
   (void)variant;
   return (g.vol + 127) / 128;
 }
+// Gauss fields shared inside a block (template flag SH of lq_gausst4_kernel): a row must be a warp and a block four
+// whole rows of one (x2, x3) column; LQ_GAUSST_NO_SHARE=1 in the environment keeps the unshared kernel (A/B)
+static inline bool lq_tuned_gausst_share_ok(const LqGeom& g) {
+  static const bool off = getenv("LQ_GAUSST_NO_SHARE") != nullptr;
+  return !off && g.ext[0] == 32 && g.ext[1] % 4 == 0 && g.vol % 128 == 0 && !g.ghost[0] && !g.ghost[1];
+}
 template <int PUSH, int RES>
 static inline void lq_tuned_gauss_titer_launch(cudaStream_t st, const LqGeom& g, const cx* U, const cx* Ein, const cx* Tin,
                                                cx* Eout, cx* Tout, double* partial, const LqPush* psE, const LqPush* psT,
@@ -1030,6 +1062,8 @@ static inline void lq_tuned_gauss_titer_launch(cudaStream_t st, const LqGeom& g,
   if (variant == 2) lq_gausst4_kernel<BLOCK, 5, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, LqFold{});
   else if (variant == 1) lq_gausst4_kernel<BLOCK, 4, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, LqFold{});
   else if (variant == 3) lq_gausst4_kernel<BLOCK, 6, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, LqFold{});
+  else if (variant == 0 && lq_tuned_gausst_share_ok(g))
+    lq_gausst4_kernel<BLOCK, 3, PUSH, RES, 0, 1><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, LqFold{});
   else lq_gausst4_kernel<BLOCK, 3, PUSH, RES, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, LqFold{});
 }
 static inline cudaError_t lq_tuned_gauss_titer(cudaStream_t st, const LqGeom& g, const cx* U, const cx* Ein, const cx* Tin,
@@ -1111,8 +1145,13 @@ static inline cudaError_t lq_tuned_gauss_titer_fold(cudaStream_t st, const LqGeo
                                                     const LqPush* psE, const LqPush* psT, const LqFold& fold) {
   constexpr int BLOCK = 128;
   const unsigned nb = (unsigned)(g.vol / BLOCK);
-  if (want_res)
+  const bool sh = lq_tuned_gausst_share_ok(g);
+  if (want_res && sh)
+    lq_gausst4_kernel<BLOCK, 3, 2, 1, 0, 1><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, fold);
+  else if (want_res)
     lq_gausst4_kernel<BLOCK, 3, 2, 1, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, fold);
+  else if (sh)
+    lq_gausst4_kernel<BLOCK, 3, 2, 0, 0, 1><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, fold);
   else
     lq_gausst4_kernel<BLOCK, 3, 2, 0, 0><<<nb, BLOCK, 0, st>>>(g, U, Ein, Tin, Eout, Tout, partial, psE, psT, fold);
   return cudaGetLastError();

@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, backend, D, gext, proc_grid, q, transport="p2p"):
+def _worker(rank, world, port, backend, D, gext, proc_grid, q, transport="p2p", flags=0):
     try:
         if ROOT not in sys.path:
             sys.path.insert(0, ROOT)
@@ -46,6 +46,8 @@ def _worker(rank, world, port, backend, D, gext, proc_grid, q, transport="p2p"):
         o = Oracle(D, gext, a=1.0, beta=6.0)
         dc = DistContext(D, gext, a=1.0, beta=6.0, proc_grid=proc_grid, lib=lib)
         c = dc.ctx
+        if flags:
+            c.set_flags(flags)
         U = o.links_random(SEED)
         E = o.momenta_refresh(SEED, 5)
         res = {}
@@ -119,11 +121,11 @@ def _worker(rank, world, port, backend, D, gext, proc_grid, q, transport="p2p"):
         raise
 
 
-def _run(world, backend, D, gext, proc_grid, transport="p2p"):
+def _run(world, backend, D, gext, proc_grid, transport="p2p", flags=0):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, D, gext, proc_grid, q, transport))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, D, gext, proc_grid, q, transport, flags))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -167,10 +169,14 @@ def test_decomposed_matches_oracle_nccl():
         assert res["transport"] == ("p2p" if transport == "p2p" else "nccl-callbacks"), res["transport"]
         if transport == "p2p":  # x0 extent 32: the bulk-copy (TMA) AoS <-> SoA row kernels on a lattice with ghost layers
             _check(_run(2, "nccl", 4, [32, 4, 4, 4], [1, 1, 1, 2], transport))
+            # opt-in: halo synchronisation folded into the MD and projection kernels (LQ_FLAG_FOLD_HALO_SYNC | 2048)
+            _check(_run(2, "nccl", 4, [32, 4, 4, 4], [1, 1, 1, 2], transport, flags=512 | 2048))
         if n >= 4:
             # 16 x 8 sites per (z, t) column: the launches with the halo synchronisation folded in cover this geometry
             res = _run(4, "nccl", 4, [16, 8, 8, 8], [1, 1, 2, 2], transport)
             _check(res)
+            if transport == "p2p":
+                _check(_run(4, "nccl", 4, [16, 8, 8, 8], [1, 1, 2, 2], transport, flags=512 | 2048))
             assert res["transport"] == ("p2p" if transport == "p2p" else "nccl-callbacks"), res["transport"]
         if n >= 8 and transport == "p2p":  # the 2(z) x 4(t) grid the 8-GPU bench runs on, incl. the zt corners
             res = _run(8, "nccl", 4, [16, 8, 8, 16], [1, 1, 2, 4], transport)

@@ -359,7 +359,7 @@ def test_snapshot_restore(backend):
     assert c.t == 5 and np.array_equal(c.links_download(), U) and np.array_equal(c.efield_download(), E)
 
 
-@pytest.mark.parametrize("ext", [[8, 8, 8, 8], [4, 6, 2, 8], [32, 4, 4, 2], [6, 4, 4, 4]])
+@pytest.mark.parametrize("ext", [[8, 8, 8, 8], [4, 6, 2, 8], [32, 4, 4, 2], [32, 8, 2, 2], [6, 4, 4, 4]])
 def test_gauss_iteration_variants_agree(backend, ext):
     """project_to_gauss (field.rs:1265-1337) through both iteration forms -- projection-step kernel then Gauss-field
     kernel (default), and the one-pass functor that recomputes the backward neighbours (LQ_FLAG_GAUSS_FUSED).  Same
