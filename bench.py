@@ -403,6 +403,21 @@ def run_ours(args):
             t = timed(fn, 3)
             sweeps[name] = {"link_updates_per_s": nl_global * 3 / (t * 1e-3), "ms_per_sweep": t / 3,
                             "hbm_frac_algorithmic": (nl_global * 3 * 1296 / (t * 1e-3)) / 1e9 / peaks()[0]}
+        # the same sweeps on a THERMALISED lattice (20 heat-bath sweeps from the hot start first): the state production
+        # sweeps run on.  The Kennedy-Pendleton rejection loop runs at warp level, so its cost depends on the state: a
+        # hot lattice (small staple determinants) rejects ~4 % of the candidates per lane, ~70 % of the warps repeat.
+        ctx.restore()
+        for i in range(20):
+            ctx.sweep_heatbath(SEED, 9100 + i)
+        therm_plaq = ctx.average_trace_plaquette().real / 3.0
+        for name, fn in (("heatbath", lambda i: ctx.sweep_heatbath(SEED, 9200 + i)),
+                         ("overrelax", lambda i: ctx.sweep_overrelax(0)),
+                         ("metropolis", lambda i: ctx.sweep_metropolis(SEED, 9700 + i))):
+            fn(0)
+            t = timed(fn, 3)
+            sweeps[name + "_thermalised"] = {"link_updates_per_s": nl_global * 3 / (t * 1e-3), "ms_per_sweep": t / 3,
+                                             "hbm_frac_algorithmic": (nl_global * 3 * 1296 / (t * 1e-3)) / 1e9 / peaks()[0],
+                                             "plaquette_over_3_before": therm_plaq}
 
     per_rank = None
     if world > 1:

@@ -26,6 +26,7 @@ SYNC_SYNC, LEAP_LEAP, SYNC_LEAP, LEAP_SYNC, SYMPLECTIC = range(5)
 OR_ROTATION, OR_REVERSE, OR_SU2_SUBGROUPS = 0, 1, 2
 FLAG_PAULI3_FIXED, FLAG_NO_KICK_MERGE, FLAG_GAUSS_FUSED, FLAG_GENERIC_KERNELS, FLAG_UNIFORM_DIRECTION = 1, 2, 4, 8, 16
 FLAG_GAUSS_TWO_PASS = 32
+FLAG_FOLD_HALO_SYNC = 512  # decomposed contexts: halo synchronisation folded into the projection kernel (| 2048: MD chain too); off by default
 INTEGRATOR_SYMPLECTIC_EULER, INTEGRATOR_OMELYAN = 0, 1
 OMELYAN_LAMBDA = 0.1931833275037836  # second-order minimum-norm coefficient (Omelyan, Mryglod, Folk 2003)
 

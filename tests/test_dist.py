@@ -136,6 +136,7 @@ def _run(world, backend, D, gext, proc_grid, transport="p2p", flags=0):
     return res
 
 
+FOLD_ALL = 512 | 2048  # LQ_FLAG_FOLD_HALO_SYNC for the projection loop and (| 2048) the MD chain
 TOL = {"roundtrip": 0.0, "hmc_acc": 0.0}
 
 
@@ -170,13 +171,13 @@ def test_decomposed_matches_oracle_nccl():
         if transport == "p2p":  # x0 extent 32: the bulk-copy (TMA) AoS <-> SoA row kernels on a lattice with ghost layers
             _check(_run(2, "nccl", 4, [32, 4, 4, 4], [1, 1, 1, 2], transport))
             # opt-in: halo synchronisation folded into the MD and projection kernels (LQ_FLAG_FOLD_HALO_SYNC | 2048)
-            _check(_run(2, "nccl", 4, [32, 4, 4, 4], [1, 1, 1, 2], transport, flags=512 | 2048))
+            _check(_run(2, "nccl", 4, [32, 4, 4, 4], [1, 1, 1, 2], transport, flags=FOLD_ALL))
         if n >= 4:
             # 16 x 8 sites per (z, t) column: the launches with the halo synchronisation folded in cover this geometry
             res = _run(4, "nccl", 4, [16, 8, 8, 8], [1, 1, 2, 2], transport)
             _check(res)
             if transport == "p2p":
-                _check(_run(4, "nccl", 4, [16, 8, 8, 8], [1, 1, 2, 2], transport, flags=512 | 2048))
+                _check(_run(4, "nccl", 4, [16, 8, 8, 8], [1, 1, 2, 2], transport, flags=FOLD_ALL))
             assert res["transport"] == ("p2p" if transport == "p2p" else "nccl-callbacks"), res["transport"]
         if n >= 8 and transport == "p2p":  # the 2(z) x 4(t) grid the 8-GPU bench runs on, incl. the zt corners
             res = _run(8, "nccl", 4, [16, 8, 8, 16], [1, 1, 2, 4], transport)
