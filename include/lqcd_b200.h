@@ -108,6 +108,18 @@ int64_t lq_kernel_launches(const lq_ctx*);         /* number of kernels this con
 /* ---- boundary marshalling (LatticeStateNew::new state.rs:779-792; set_link_matrix :808-815) ----------------- */
 int lq_links_upload(lq_ctx*, const double* aos, int64_t n_links);   /* LQ_E_SIZE if n_links mismatches */
 int lq_links_download(lq_ctx*, double* aos, int64_t n_links);
+/* Pipelined marshalling for a host that streams a batch of independent configurations through one context (same
+ * layouts and reference calls as lq_links_upload / _download: LatticeStateNew::new, link_matrix(), state.rs:779-815).
+ * upload_begin starts copying `aos` into a device staging buffer on a copy stream and returns at once (pinned host
+ * memory makes the copy asynchronous); upload_commit makes the staged links the state's links, ordered after the copy.
+ * download_begin snapshots the links into a second staging buffer and starts copying them to `aos` on another copy
+ * stream.  lq_copies_wait blocks until every begun copy has finished: only then may the host arrays be reused / read.
+ * One upload and one download in flight at a time (LQ_E_BADARG otherwise).  PCIe is idle while a trajectory computes and
+ * full duplex, so the next input and the previous result travel behind the kernels (bench.py e2e leg). */
+int lq_links_upload_begin(lq_ctx*, const double* aos, int64_t n_links);
+int lq_links_upload_commit(lq_ctx*);
+int lq_links_download_begin(lq_ctx*, double* aos, int64_t n_links);
+int lq_copies_wait(lq_ctx*);
 int lq_efield_upload(lq_ctx*, const double* aos, int64_t n_links);
 int lq_efield_download(lq_ctx*, double* aos, int64_t n_links);
 /* same, from / to DEVICE memory already in the reference AoS layout (no PCIe copy) */

@@ -70,6 +70,10 @@ SYMBOLS = {
     "lq_kernel_launches": (C.c_int64, [_vp]),
     "lq_links_upload": (C.c_int, [_vp, _dp, C.c_int64]),
     "lq_links_download": (C.c_int, [_vp, _dp, C.c_int64]),
+    "lq_links_upload_begin": (C.c_int, [_vp, _dp, C.c_int64]),
+    "lq_links_upload_commit": (C.c_int, [_vp]),
+    "lq_links_download_begin": (C.c_int, [_vp, _dp, C.c_int64]),
+    "lq_copies_wait": (C.c_int, [_vp]),
     "lq_efield_upload": (C.c_int, [_vp, _dp, C.c_int64]),
     "lq_efield_download": (C.c_int, [_vp, _dp, C.c_int64]),
     "lq_links_upload_device": (C.c_int, [_vp, _vp, C.c_int64]),
@@ -314,6 +318,25 @@ class Context:
         assert U.dtype == np.float64 and U.flags["C_CONTIGUOUS"] and U.size == self.nl * 18
         self._check(self.lib.lq_links_download(self._h, _p(U), self.nl), "lq_links_download")
         return U
+
+    # pipelined marshalling: the arrays must stay alive and untouched until copies_wait() (use pinned memory for copies
+    # that really run behind the kernels)
+    def links_upload_begin(self, U):
+        assert U.dtype == np.float64 and U.flags["C_CONTIGUOUS"] and U.size == self.nl * 18
+        self._inflight_up = U
+        self._check(self.lib.lq_links_upload_begin(self._h, _p(U), self.nl), "lq_links_upload_begin")
+
+    def links_upload_commit(self):
+        self._check(self.lib.lq_links_upload_commit(self._h), "lq_links_upload_commit")
+
+    def links_download_begin(self, out):
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == self.nl * 18
+        self._inflight_down = out
+        self._check(self.lib.lq_links_download_begin(self._h, _p(out), self.nl), "lq_links_download_begin")
+
+    def copies_wait(self):
+        self._check(self.lib.lq_copies_wait(self._h), "lq_copies_wait")
+        self._inflight_up = self._inflight_down = None
 
     def efield_upload(self, E):
         E = _f64(E)

@@ -137,6 +137,14 @@ struct lq_ctx {
   void* p2p_base[LQ_P2P_MAXNB][LQ_P2P_NBUF];      // opened peer buffers (per unique peer)
   int64_t p2p_exchanges;
   void* d_push;                                   // LqPush[8] on the device: peer table per field-buffer allocation
+  // pipelined marshalling (lq_links_upload_begin / _commit, lq_links_download_begin, lq_copies_wait)
+  double *stage_in, *stage_out;  // AoS staging buffers on the device
+  bool up_pending;
+#ifndef LQ_HOST_EMU
+  cudaStream_t s_h2d, s_d2h;
+  cudaEvent_t ev_in_ready, ev_in_consumed, ev_out_ready, ev_out_done;
+  bool copy_streams;
+#endif
   unsigned int* d_fold_counter;                   // boundary blocks finished (halo synchronisation folded into the kernels)
   bool p2p_pending;                               // the last folded launch released an epoch nobody has acquired yet
   // optional per-kernel-class CUDA-event timing (lq_profile_*)
@@ -559,6 +567,18 @@ int lq_ctx_destroy(lq_ctx* c) {
   rt_free(c->p2p_flags);
   rt_free(c->d_push);
   rt_free(c->d_fold_counter);
+  rt_free(c->stage_in);
+  rt_free(c->stage_out);
+#ifndef LQ_HOST_EMU
+  if (c->copy_streams) {
+    cudaStreamDestroy(c->s_h2d);
+    cudaStreamDestroy(c->s_d2h);
+    cudaEventDestroy(c->ev_in_ready);
+    cudaEventDestroy(c->ev_in_consumed);
+    cudaEventDestroy(c->ev_out_ready);
+    cudaEventDestroy(c->ev_out_done);
+  }
+#endif
 #endif
   rt_free(c->snapU);
   rt_free(c->snapE);
@@ -691,6 +711,86 @@ int lq_links_download(lq_ctx* c, double* aos, int64_t n_links) {
   LQ_TRY(links_to_device_aos(c, c->d_aos));
   LQ_TRY(rt_copy(aos, c->d_aos, bytes, D2H, c->stream));
   return rt_sync(c->stream);
+}
+// ---- pipelined marshalling: the host <-> device copies of consecutive, independent states overlap the kernels.
+// A host that streams a batch of configurations through one context (measurement runs over a stored ensemble; the e2e leg
+// of bench.py) begins the upload of the NEXT configuration and the download of the PREVIOUS result while the current
+// trajectory computes: PCIe is idle during compute and full duplex.  Two staging buffers and two copy streams; events order
+// the transpositions (context stream) against the copies.
+#ifndef LQ_HOST_EMU
+static int copy_streams(lq_ctx* c) {
+  if (c->copy_streams) return LQ_OK;
+  LQ_CHECK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  LQ_CHECK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  LQ_CHECK(cudaEventCreateWithFlags(&c->ev_in_ready, cudaEventDisableTiming));
+  LQ_CHECK(cudaEventCreateWithFlags(&c->ev_in_consumed, cudaEventDisableTiming));
+  LQ_CHECK(cudaEventCreateWithFlags(&c->ev_out_ready, cudaEventDisableTiming));
+  LQ_CHECK(cudaEventCreateWithFlags(&c->ev_out_done, cudaEventDisableTiming));
+  c->copy_streams = true;
+  return LQ_OK;
+}
+#endif
+int lq_links_upload_begin(lq_ctx* c, const double* aos, int64_t n_links) {
+  if (!c || !aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  if (c->up_pending) return LQ_E_BADARG;  // one upload in flight at a time
+  LQ_GUARD(c);
+  const size_t bytes = (size_t)n_links * 18 * sizeof(double);
+  if (!c->stage_in) LQ_TRY(rt_malloc((void**)&c->stage_in, bytes));
+#ifndef LQ_HOST_EMU
+  LQ_TRY(copy_streams(c));
+  LQ_CHECK(cudaStreamWaitEvent(c->s_h2d, c->ev_in_consumed, 0));  // the previous commit is done reading the staging buffer
+  LQ_CHECK(cudaMemcpyAsync(c->stage_in, aos, bytes, cudaMemcpyHostToDevice, c->s_h2d));
+  LQ_CHECK(cudaEventRecord(c->ev_in_ready, c->s_h2d));
+#else
+  memcpy(c->stage_in, aos, bytes);
+#endif
+  c->up_pending = true;
+  return LQ_OK;
+}
+int lq_links_upload_commit(lq_ctx* c) {
+  if (!c || !c->up_pending) return LQ_E_BADARG;
+  LQ_GUARD(c);
+#ifndef LQ_HOST_EMU
+  LQ_CHECK(cudaStreamWaitEvent(c->stream, c->ev_in_ready, 0));
+#endif
+  LQ_TRY(links_from_device_aos(c, c->stage_in));
+#ifndef LQ_HOST_EMU
+  LQ_CHECK(cudaEventRecord(c->ev_in_consumed, c->stream));
+#endif
+  c->up_pending = false;
+  return LQ_OK;
+}
+int lq_links_download_begin(lq_ctx* c, double* aos, int64_t n_links) {
+  if (!c || !aos) return LQ_E_BADARG;
+  if (n_links != lq_num_links(c)) return LQ_E_SIZE;
+  LQ_GUARD(c);
+  const size_t bytes = (size_t)n_links * 18 * sizeof(double);
+  if (!c->stage_out) LQ_TRY(rt_malloc((void**)&c->stage_out, bytes));
+#ifndef LQ_HOST_EMU
+  LQ_TRY(copy_streams(c));
+  LQ_CHECK(cudaStreamWaitEvent(c->stream, c->ev_out_done, 0));  // the previous download has left the staging buffer
+  LQ_TRY(links_to_device_aos(c, c->stage_out));
+  LQ_CHECK(cudaEventRecord(c->ev_out_ready, c->stream));
+  LQ_CHECK(cudaStreamWaitEvent(c->s_d2h, c->ev_out_ready, 0));
+  LQ_CHECK(cudaMemcpyAsync(aos, c->stage_out, bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+  LQ_CHECK(cudaEventRecord(c->ev_out_done, c->s_d2h));
+#else
+  LQ_TRY(links_to_device_aos(c, c->stage_out));
+  memcpy(aos, c->stage_out, bytes);
+#endif
+  return LQ_OK;
+}
+int lq_copies_wait(lq_ctx* c) {
+  if (!c) return LQ_E_BADARG;
+  LQ_GUARD(c);
+#ifndef LQ_HOST_EMU
+  if (c->copy_streams) {
+    LQ_CHECK(cudaStreamSynchronize(c->s_h2d));
+    LQ_CHECK(cudaStreamSynchronize(c->s_d2h));
+  }
+#endif
+  return LQ_OK;
 }
 int lq_efield_upload(lq_ctx* c, const double* aos, int64_t n_links) {
   if (!c || !aos) return LQ_E_BADARG;

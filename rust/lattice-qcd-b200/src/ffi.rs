@@ -42,6 +42,11 @@ extern "C" {
     /// LatticeStateNew::new / set_link_matrix (state.rs:779-815)
     pub fn lq_links_upload(c: *mut lq_ctx, aos: *const c_double, n_links: i64) -> c_int;
     pub fn lq_links_download(c: *mut lq_ctx, aos: *mut c_double, n_links: i64) -> c_int;
+    // pipelined marshalling (a batch of configurations streamed through one context)
+    pub fn lq_links_upload_begin(c: *mut lq_ctx, aos: *const c_double, n_links: i64) -> c_int;
+    pub fn lq_links_upload_commit(c: *mut lq_ctx) -> c_int;
+    pub fn lq_links_download_begin(c: *mut lq_ctx, aos: *mut c_double, n_links: i64) -> c_int;
+    pub fn lq_copies_wait(c: *mut lq_ctx) -> c_int;
     pub fn lq_efield_upload(c: *mut lq_ctx, aos: *const c_double, n_links: i64) -> c_int;
     pub fn lq_efield_download(c: *mut lq_ctx, aos: *mut c_double, n_links: i64) -> c_int;
     pub fn lq_links_set_cold(c: *mut lq_ctx) -> c_int;

@@ -359,6 +359,36 @@ def test_snapshot_restore(backend):
     assert c.t == 5 and np.array_equal(c.links_download(), U) and np.array_equal(c.efield_download(), E)
 
 
+@pytest.mark.parametrize("ext", [[4, 4, 4, 4], [32, 4, 2, 2]])
+def test_pipelined_marshalling(backend, ext):
+    """lq_links_upload_begin / _commit, lq_links_download_begin, lq_copies_wait: the same bytes as the synchronous calls
+    (LatticeStateNew::new, link_matrix(), state.rs:779-815), with the next upload begun before the previous download ends."""
+    o = Oracle(4, ext, a=1.0, beta=6.0)
+    c = backend(4, ext, a=1.0, beta=6.0)
+    inputs = [o.links_random(SEED_RNG, k) for k in range(3)]
+    outs = [np.empty_like(inputs[0]) for _ in range(3)]
+    E = o.momenta_refresh(SEED_RNG, 2)
+    ref = []
+    for U in inputs:  # the serial sequence
+        c.links_upload(U)
+        c.efield_upload(E)
+        c.symplectic_n(0.01, 2)
+        ref.append(c.links_download().copy())
+    c.links_upload_begin(inputs[0])
+    for k in range(3):
+        c.links_upload_commit()
+        if k + 1 < 3:
+            c.links_upload_begin(inputs[k + 1])  # travels while step k computes
+        c.efield_upload(E)
+        c.symplectic_n(0.01, 2)
+        c.links_download_begin(outs[k])
+    c.copies_wait()
+    for k in range(3):
+        assert np.array_equal(outs[k], ref[k])
+    with pytest.raises(Exception):
+        c.links_upload_commit()  # nothing begun
+
+
 @pytest.mark.parametrize("ext", [[8, 8, 8, 8], [4, 6, 2, 8], [32, 4, 4, 2], [32, 8, 2, 2], [6, 4, 4, 4]])
 def test_gauss_iteration_variants_agree(backend, ext):
     """project_to_gauss (field.rs:1265-1337) through both iteration forms -- projection-step kernel then Gauss-field
