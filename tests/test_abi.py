@@ -28,6 +28,22 @@ def test_library_exports_every_declared_symbol():
     _capi.load()  # binds every symbol with its argument types
 
 
+def test_python_constants_match_the_header_enums():
+    """LQ_FLAG_*, LQ_OR_*, integrator and error-code values in include/lqcd_b200.h are the ones the ctypes binding uses."""
+    from lattice_qcd_rs_b200 import _capi
+    src = open(os.path.join(ROOT, "include", "lqcd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    enums = {k: int(v) for k, v in re.findall(r"\b(LQ_[A-Z0-9_]+)\s*=\s*(-?\d+)", src)}
+    assert enums["LQ_FLAG_FOLD_HALO_SYNC"] == 512
+    for name, value in enums.items():
+        if name.startswith("LQ_FLAG_"):
+            py = getattr(_capi, name[3:], None)
+            assert py == value, (name, value, py)
+        elif name.startswith("LQ_OR_"):
+            assert getattr(_capi, name[3:]) == value, name
+    assert _capi.INTEGRATOR_OMELYAN == enums["LQ_INTEGRATOR_OMELYAN"]
+
+
 def test_rust_shim_binds_only_declared_symbols():
     ffi = open(os.path.join(ROOT, "rust", "lattice-qcd-b200", "src", "ffi.rs")).read()
     used = set(re.findall(r"pub fn (lq_[a-z0-9_]+)", ffi))
