@@ -7,45 +7,62 @@ import itertools
 
 
 def geom(e, ghost, bs, zfirst):
-    e0,e1,e2,e3=e; g2,g3=ghost
-    if not g2 and not g3: return None
-    colsites=e0*e1
-    vol=e0*e1*e2*e3
-    if colsites%bs or vol%bs: return None
-    n3=(2 if e3>=2 else 1) if g3 else 0
-    n2=(2 if e2>=2 else 1) if g2 else 0
-    colB=n3*e2+(e3-n3)*n2
-    bpc=colsites//bs; total=e2*e3*bpc; nB=colB*bpc
-    if nB<=0 or nB>total: return None
-    zf=1 if (zfirst or n3==0) else 0
-    nF=nB if zf else n3*e2*bpc
-    sp=total//nF
-    S=1 if sp<1 else (4 if sp>4 else sp)
-    return dict(bpc=bpc,nB=nB,nF=nF,S=S,zfirst=zf,total=total,n2=n2,n3=n3)
-def block(e,f,blk):
-    e0,e1,e2,e3=e; n2,n3=f["n2"],f["n3"]
-    S=f["S"]; j=blk//S
-    if blk-j*S==0 and j<f["nF"]:
-        isb=True
-        cb=j//f["bpc"]; within=j-cb*f["bpc"]
-        p1=n3*e2
-        if cb<p1:
-            q=cb//e2; x3=0 if q==0 else e3-1; x2=cb-q*e2
+    """lq_fold_geom: schedule of a kernel whose blocks hold `bs` consecutive sites; None: geometry not covered."""
+    e0, e1, e2, e3 = e
+    g2, g3 = ghost
+    if not g2 and not g3:
+        return None
+    colsites = e0 * e1
+    if colsites % bs or (colsites * e2 * e3) % bs:
+        return None
+    n3 = (2 if e3 >= 2 else 1) if g3 else 0  # boundary values of x3, x2
+    n2 = (2 if e2 >= 2 else 1) if g2 else 0
+    col_b = n3 * e2 + (e3 - n3) * n2
+    bpc = colsites // bs
+    total, n_b = e2 * e3 * bpc, col_b * bpc
+    if n_b <= 0 or n_b > total:
+        return None
+    zf = 1 if (zfirst or n3 == 0) else 0
+    n_f = n_b if zf else n3 * e2 * bpc
+    sp = total // n_f
+    return dict(bpc=bpc, nB=n_b, nF=n_f, S=min(max(sp, 1), 4), zfirst=zf, total=total, n2=n2, n3=n3)
+
+
+def block(e, f, blk):
+    """lq_fold_block: grid position -> (natural block index, block of a boundary column?)."""
+    _, _, e2, e3 = e
+    n2, n3, s, bpc = f["n2"], f["n3"], f["S"], f["bpc"]
+    j = blk // s
+    if blk - j * s == 0 and j < f["nF"]:
+        isb = True
+        cb = j // bpc
+        within = j - cb * bpc
+        p1 = n3 * e2
+        if cb < p1:
+            q = cb // e2
+            x3 = 0 if q == 0 else e3 - 1
+            x2 = cb - q * e2
         else:
-            r=cb-p1; q=r//n2; x3=(1 if n3 else 0)+q; x2=0 if r-q*n2==0 else e2-1
-        col=x2+e2*x3
+            r = cb - p1
+            q = r // n2
+            x3 = (1 if n3 else 0) + q
+            x2 = 0 if r - q * n2 == 0 else e2 - 1
+        col = x2 + e2 * x3
     else:
-        ji=blk-min((blk+S-1)//S,f["nF"])
-        ci=ji//f["bpc"]; within=ji-ci*f["bpc"]
+        ji = blk - min((blk + s - 1) // s, f["nF"])
+        ci = ji // bpc
+        within = ji - ci * bpc
         if f["zfirst"]:
-            isb=False
-            i2=e2-n2; q=ci//i2
-            col=(1 if n2 else 0)+(ci-q*i2)+e2*((1 if n3 else 0)+q)
+            isb = False
+            i2 = e2 - n2
+            q = ci // i2
+            col = (1 if n2 else 0) + (ci - q * i2) + e2 * ((1 if n3 else 0) + q)
         else:
-            q=ci//e2; x2=ci-q*e2
-            isb=bool(n2 and (x2==0 or x2==e2-1))
-            col=x2+e2*((1 if n3 else 0)+q)
-    return col*f["bpc"]+within,isb
+            q = ci // e2
+            x2 = ci - q * e2
+            isb = bool(n2 and x2 in (0, e2 - 1))
+            col = x2 + e2 * ((1 if n3 else 0) + q)
+    return col * bpc + within, isb
 
 
 def test_fold_schedule_is_a_permutation_with_the_right_boundary_set():
