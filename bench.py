@@ -2,7 +2,9 @@
 """bench.py -- HMC link-updates/sec at 32^4, f64, on N B200s (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config metric|c4|c5|d3]
-  (N > 1: launched by torch.distributed.run, one rank per GPU)
+  (N > 1: launched by torch.distributed.run, one rank per GPU; a CUDA-vs-oracle parity block on a small lattice over the
+   same process grid runs before timing and is printed as "parity"; "per_rank" lists every rank's kernel times)
+  --flags: LQ_FLAG_* bits for A/B runs (512 | 2048: halo synchronisation folded into the kernels; 32: two-pass Gauss loop)
 
 A "step" is one HMC trajectory of HybridMonteCarloDiagnostic::next_element (hybrid_monte_carlo.rs:465-471, 573-613):
 momentum refresh -> Gauss projection -> H_old -> 100 symplectic-Euler MD steps (dt = 0.01, the reference's own HMC
@@ -22,8 +24,10 @@ free-running chain drifts and its Gauss iteration count climbs with the trajecto
 --config d3: BASELINE config 5b, the dimension-generic API on a D = 3 40^3 lattice (single GPU).
 
 value : device-resident (links stay in HBM between trajectories), CUDA events on the context stream, max over ranks.
-e2e   : the same trajectory through the C ABI with HOST buffers: links uploaded from pinned host memory before and
-        downloaded after every trajectory, inside the timed region.
+e2e   : the same trajectory through the C ABI with HOST buffers: every step uploads its links from and downloads its result
+        to pinned host memory inside the timed region, through the pipelined marshalling calls (the upload of step k+1 and
+        the download of step k travel while step k computes); e2e.serial_calls: the synchronous upload -> trajectory ->
+        download sequence; e2e.host_copies_alone: the copies without any compute.
 --impl reference : the CPU restatement of the reference loops (oracle/, OpenMP over all host cores; the Rust crate
         cannot be built in this image) on a bounded sample of the same 32^4 workload (see CpuSample).
 """
