@@ -58,6 +58,16 @@ BYTES_FUSED = 416
 FLOPS_FUSED = 13 * 216 + 60 + 280
 
 
+def workload_text(config, L):
+    """The workload both arms name in config.workload (the reference arm runs a bounded sample of it: cpu_baseline.sample)."""
+    name = {"metric": f"{L}^4 per GPU", "c4": "BASELINE config 4: ONE 48^3 x 96 lattice over all GPUs",
+            "c5": "BASELINE config 5: ONE 64^4 lattice over all GPUs",
+            "d3": "BASELINE config 5b: D = 3, 40^3, dimension-generic kernels"}[config]
+    return (f"{name}, beta={BETA}, a={SPACING}: full HMC trajectory (refresh sigma=0.5/beta, Gauss projection, 2x H_total, "
+            f"{MD_STEPS} symplectic-Euler steps dt={DT}, accept/reject) + normalize_link_matrices; hot start (Philox random "
+            "SU(3)); every step repeats the SAME trajectory from a device snapshot (pinned workload)")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -189,8 +199,7 @@ def run_reference(args):
         "impl": "reference", "metric": "HMC link-updates/sec at 32^4 f64", "value": val, "unit": "link-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.extent}^4 beta={BETA} HMC ({MD_STEPS} MD steps/trajectory), hot start",
-                   "sample": cpu["sample"]},
+        "config": {"workload": workload_text("metric", args.extent), "config": "metric", "sample": cpu["sample"]},
         "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": "link-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -502,18 +511,12 @@ def run_ours(args):
     breakdown["sum_of_kernels"] = sum(breakdown.values())
     breakdown["total"] = ms / steps
     breakdown["unaccounted_host_sync_and_restore"] = breakdown["total"] - breakdown["sum_of_kernels"]
-    workload_name = {"metric": f"{L}^4 per GPU", "c4": "BASELINE config 4: ONE 48^3 x 96 lattice over all GPUs",
-                     "c5": "BASELINE config 5: ONE 64^4 lattice over all GPUs",
-                     "d3": "BASELINE config 5b: D = 3, 40^3, dimension-generic kernels"}[args.config]
     line = {
         "metric": "HMC link-updates/sec at 32^4 f64", "value": value, "unit": "link-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"{workload_name}, beta={BETA}, a={SPACING}: full HMC trajectory (refresh sigma=0.5/beta, Gauss "
-                        f"projection, 2x H_total, {MD_STEPS} symplectic-Euler steps dt={DT}, accept/reject) + "
-                        "normalize_link_matrices; hot start (Philox random SU(3)); every step repeats the SAME trajectory "
-                        "from a device snapshot (pinned workload)",
+            "workload": workload_text(args.config, L),
             "config": args.config, "global_extent": gext, "local_extent": ctx.extent, "proc_grid": pg, "parallelism": par,
             "l2": "inputs (604 MB links + 268 MB E-field per GPU at 32^4) exceed the 126 MB L2; no flush needed",
             "md_steps_per_trajectory": MD_STEPS,
