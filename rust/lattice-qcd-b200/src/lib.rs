@@ -157,6 +157,28 @@ impl<const D: usize> LatticeStateCuda<D> {
     pub fn to_default(&self) -> Result<LatticeStateDefault<D>, StateInitializationError> {
         LatticeStateDefault::new(self.lattice.clone(), self.beta, self.ctx.download_links())
     }
+    /// Streaming a batch of configurations through one device state (include/lqcd_b200.h, "pipelined marshalling"):
+    /// start copying the NEXT configuration to the device while the current one is still being worked on.  `next` must
+    /// stay alive and unmodified until `commit_links` has been followed by `wait_copies` (the borrow enforces the first
+    /// half; keep the owner around for the second).  Pinned host memory makes the copy run behind the kernels.
+    pub fn begin_set_link_matrix(&mut self, next: &LinkMatrix) -> Result<(), CudaError> {
+        assert_eq!(next.len(), self.ctx.n_links(), "link matrix of the wrong size (state.rs:808-815 panics too)");
+        check(unsafe { ffi::lq_links_upload_begin(self.ctx.0, next.as_slice().as_ptr() as *const f64, next.len() as i64) })
+    }
+    /// The links begun with `begin_set_link_matrix` become the state's links (LatticeState::set_link_matrix, state.rs:808-815).
+    pub fn commit_links(&mut self) -> Result<(), CudaError> {
+        self.host_links = OnceLock::new();
+        check(unsafe { ffi::lq_links_upload_commit(self.ctx.0) })
+    }
+    /// Start copying the current links into `out` (link_matrix() without blocking); valid after `wait_copies`.
+    pub fn begin_download_links(&self, out: &mut [CMatrix3]) -> Result<(), CudaError> {
+        assert_eq!(out.len(), self.ctx.n_links());
+        check(unsafe { ffi::lq_links_download_begin(self.ctx.0, out.as_mut_ptr() as *mut f64, out.len() as i64) })
+    }
+    /// Block until every begun copy has finished.
+    pub fn wait_copies(&self) -> Result<(), CudaError> {
+        check(unsafe { ffi::lq_copies_wait(self.ctx.0) })
+    }
 }
 
 impl<const D: usize> Clone for LatticeStateCuda<D> {
